@@ -1,0 +1,185 @@
+/*
+ * sg_b200.h — C ABI of libsg_b200.so, the B200 (sm_100a) implementation of the
+ * string_grouper hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (Bergvca/string_grouper @ 270044e9, pure Python) has no FFI of
+ * its own: its hot path calls scikit-learn and sparse_dot_topn.  Every entry
+ * point below names the reference interface it replaces as
+ * /root/reference/string_grouper/string_grouper.py:<line> ("sg.py:<line>").
+ *
+ * Conventions
+ *   - every pointer marked [dev] is device memory owned by the caller
+ *     (allocated through torch in the Python host side);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     there are no hidden synchronisations; counters the host needs are left in
+ *     device memory and the host reads them back when it chooses to;
+ *   - return value: SG_OK or a negative SG_ERR_*; sg_last_error() gives the
+ *     text for the calling thread; nothing throws across the ABI;
+ *   - two-phase sizing: *_workspace_bytes() then the call with `ws`.
+ */
+#ifndef SG_B200_H
+#define SG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_OK 0
+#define SG_ERR_INVALID (-1)     /* -> ValueError   */
+#define SG_ERR_CUDA (-2)        /* -> RuntimeError */
+#define SG_ERR_OVERFLOW (-3)    /* -> OverflowError (caught by fit(), sg.py:400) */
+#define SG_ERR_UNSUPPORTED (-4) /* -> NotImplementedError */
+
+#define SG_DTYPE_F32 0
+#define SG_DTYPE_F64 1
+
+/* analyzer flags for sg_tfidf_* (sg.py:365-378) */
+#define SG_FLAG_IGNORE_CASE 1u   /* fold A-Z to a-z                                  */
+#define SG_FLAG_STRIP_DEFAULT 2u /* delete the default regex class  [,-./]|\s         */
+
+const char *sg_last_error(void);
+int sg_abi_version(void);
+/* SM count, opt-in shared memory per block, L2 bytes of the current device. */
+int sg_device_info(int *sm_count, int *smem_optin_bytes, int *l2_bytes);
+
+/* ------------------------------------------------------------------------- *
+ * K1 — character n-gram TF-IDF, CSR emitted in HBM.
+ * Replaces: StringGrouper.n_grams (sg.py:365-378) + TfidfVectorizer fit /
+ * transform (sg.py:305-308, :685-707; sklearn text.py:_count_vocab, idf,
+ * l2 normalise).  Input is the concatenation master ++ duplicates as UTF-8
+ * bytes that are already pure ASCII (the Python host has run lower()/NFKD on
+ * the rare non-ASCII rows, exactly sg.py:372-375), with n_docs+1 offsets.
+ *
+ * Phase 1 (sg_tfidf_count): per document: strip/fold bytes, pack n-grams into
+ * order-preserving keys (7 bits per char, big endian), sort + unique + count
+ * inside the warp, add 1 to df[key] per distinct key, store the (key,tf)
+ * runs at the document's byte offset in `scratch_*` and the run length in
+ * `row_nnz`.  `df_table` has 2^(7*ngram) int32 slots (ngram <= 4) and must be
+ * zeroed by the caller.
+ * ------------------------------------------------------------------------- */
+int64_t sg_tfidf_table_slots(int ngram);
+int sg_tfidf_count(const uint8_t *bytes /*[dev]*/, const int64_t *offsets /*[dev] n_docs+1*/,
+                   int64_t n_docs, int ngram, unsigned flags,
+                   int32_t *df_table /*[dev] slots, zeroed*/,
+                   uint32_t *scratch_key /*[dev] total_bytes*/, uint16_t *scratch_tf /*[dev] total_bytes*/,
+                   int32_t *row_nnz /*[dev] n_docs*/, void *stream);
+
+/*
+ * Phase 2 (sg_tfidf_finalize): exclusive scan of row_nnz -> indptr (int64),
+ * exclusive scan of (df>0) over the key table -> column id = rank of the
+ * n-gram in sorted order (sklearn _sort_features), idf = ln((1+n)/(1+df))+1,
+ * x = tf*idf, row L2 norm accumulated in double in column order, IEEE sqrt
+ * and divide; writes indices + f64 values + f32 values of all n_docs rows.
+ * `vocab_size` [dev] receives V.  `nnz_total` [dev] receives indptr[n_docs].
+ * The caller sizes `indices/val64/val32` with total_bytes entries (an upper
+ * bound of nnz), so no host read-back is needed between the phases.
+ */
+size_t sg_tfidf_finalize_workspace_bytes(int64_t n_docs, int ngram);
+int sg_tfidf_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs, int ngram, int dtype,
+                      int32_t *df_table /*[dev] in: df, out: rank (column id)*/,
+                      const uint32_t *scratch_key, const uint16_t *scratch_tf,
+                      const int32_t *row_nnz,
+                      int64_t *indptr /*[dev] n_docs+1*/, int32_t *indices /*[dev]*/,
+                      double *val64 /*[dev]*/, float *val32 /*[dev]*/,
+                      int32_t *vocab_size /*[dev] 1*/, int64_t *nnz_total /*[dev] 1*/,
+                      void *ws /*[dev]*/, size_t ws_bytes, void *stream);
+
+/* Sorted vocabulary keys (for get_feature_names-style inspection and tests). */
+int sg_tfidf_vocab_keys(const int32_t *df_rank_table /*[dev] after finalize*/, int ngram,
+                        const int32_t *df_raw /*[dev] copy of df before finalize, may be NULL*/,
+                        uint32_t *keys_out /*[dev] V*/, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2 — blocked CSR x CSR^T, thresholded, top-n per left row.
+ * Replaces: StringGrouper._build_matches (sg.py:709-752), i.e. the
+ * sp_matmul_topn block products (:737-743), the zip over right blocks (:746)
+ * and the vstack over left blocks (:750).
+ * ------------------------------------------------------------------------- */
+
+/* number of column tiles for `n_right` rows at `tile_w` columns per tile */
+int64_t sg_num_tiles(int64_t n_right, int tile_w);
+
+/*
+ * Right matrix -> tile-bucketed postings (the transpose that sp_matmul_topn
+ * performs on `Bi.T`, sg.py:727/:738, done once and laid out for the kernel):
+ * bucket (f, t) holds the (doc, weight) pairs of feature f whose doc lies in
+ * column tile t; bucket_ptr has n_cols*T+1 entries; postings are 8 bytes
+ * {int32 doc, float w}.
+ */
+size_t sg_postings_workspace_bytes(int64_t n_cols, int64_t n_tiles);
+int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr /*[dev]*/,
+                      const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/, int tile_w,
+                      int32_t *bucket_ptr /*[dev] n_cols*T+1*/, void *postings /*[dev] nnz*8 B*/,
+                      void *ws /*[dev]*/, size_t ws_bytes, void *stream);
+
+/*
+ * Candidate generation: for left rows [row_begin,row_end) stream the posting
+ * buckets of the row's features into a per-warp shared-memory accumulator tile
+ * (fp32), sweep each column tile and append every (row, col) whose fp32 score
+ * exceeds `cand_threshold` (= min_similarity - margin, clamped at 0) to the
+ * candidate list.  `cand_count` [dev] (zeroed by the caller) ends up holding
+ * the number of candidates FOUND, which may exceed `cand_cap` (then only the
+ * first cand_cap were stored and the caller re-runs with a larger buffer).
+ * `row_queue` [dev] (zeroed) is the dynamic work queue.
+ * smem_bytes_hint: 0 = pick the largest configuration the device allows.
+ */
+int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_indices /*[dev]*/,
+                         const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
+                         int64_t n_right, int64_t n_cols, const int32_t *bucket_ptr /*[dev]*/,
+                         const void *postings /*[dev]*/, int tile_w, float cand_threshold,
+                         int32_t *cand_row /*[dev] cap*/, int32_t *cand_col /*[dev] cap*/,
+                         int64_t cand_cap, unsigned long long *cand_count /*[dev] 1*/,
+                         int32_t *row_queue /*[dev] 1*/, int warps_per_cta, void *stream);
+
+/*
+ * Exact re-scoring of the candidates: sorted-merge dot product of left row i
+ * and right row j in ascending feature order (the accumulation order of
+ * sp_matmul_topn) in the matrix dtype (f64 default, sg.py:18), multiply and
+ * add rounded separately (no FMA contraction) so that scores equal the CPU
+ * path bit for bit.
+ */
+int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
+               const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
+               const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
+               double *score_out /*[dev] n_cand*/, void *stream);
+
+/*
+ * Per-row selection: keep score > threshold (strict, sg.py:729/:740), at most
+ * top_n per left row (largest first; ties: smaller column first), rows are
+ * emitted in ascending order, entries inside a row by descending score
+ * (sort=True, sg.py:730/:741).  Row ids are relative to `row_begin`.
+ * Outputs: out_indptr (int64, n_rows+1), out_row/out_col/out_score with
+ * capacity n_cand; `out_nnz` [dev] and `out_max_row` [dev] (= the value of
+ * fit()'s _true_max_n_matches, sg.py:417).
+ */
+size_t sg_topn_select_workspace_bytes(int64_t n_cand, int64_t n_rows);
+int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
+                   const double *score, int64_t row_begin, int64_t n_rows, int top_n,
+                   double threshold, int64_t *out_indptr, int32_t *out_row, int32_t *out_col,
+                   double *out_score, int64_t *out_nnz /*[dev] 1*/, int32_t *out_max_row /*[dev] 1*/,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4 — self-match post-processing.
+ * Replaces: _fix_diagonal + _symmetrize_matrix on LIL (sg.py:419-427,
+ * :955-964): diagonal := 1 for every row, pattern := pattern U pattern^T,
+ * output ordered by (row, col) ascending like tolil().tocsr().
+ * Output capacity needed: 2*nnz_in + n.
+ * ------------------------------------------------------------------------- */
+size_t sg_symmetrize_workspace_bytes(int64_t nnz_in, int64_t n);
+int sg_symmetrize(int64_t n, int64_t nnz_in, const int32_t *in_row, const int32_t *in_col,
+                  const double *in_score, int32_t *out_row, int32_t *out_col, double *out_score,
+                  int64_t *out_nnz /*[dev] 1*/, void *ws, size_t ws_bytes, void *stream);
+
+/* row-wise dot of two CSR matrices of equal shape (StringGrouper.dot, sg.py:433-440) */
+int sg_rowwise_dot(int64_t n_rows, const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
+                   const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
+                   double *out /*[dev] n_rows*/, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG_B200_H */

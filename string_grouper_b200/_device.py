@@ -1,0 +1,323 @@
+"""Device-side plumbing: HBM containers (torch tensors) and the calls into libsg_b200.so.
+
+PyTorch is used for device memory, streams and (in _dist.py) torch.distributed
+only; every kernel on the hot path lives in csrc/*.cu behind the C ABI.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+
+_TORCH = None
+
+# launch statistics of the last calls, read by bench.py ("gpu_launches")
+LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
+                 "rowdot": 0}
+
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "3072"))
+DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "16"))
+CAND_MARGIN = 2.0e-4   # fp32 candidate scores are re-scored exactly; see DESIGN.md §K2
+
+
+def torch():
+    global _TORCH
+    if _TORCH is None:
+        import torch as _t
+        _TORCH = _t
+    return _TORCH
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise _lib.SgB200Error("string_grouper_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback "
+                               "for the hot path")
+    _lib.load()
+    return t
+
+
+def _ptr(x):
+    return ctypes.c_void_p(0 if x is None else x.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def _empty(n, dtype, device):
+    return torch().empty(max(int(n), 1), dtype=dtype, device=device)
+
+
+class DeviceCSR:
+    """CSR matrix resident in HBM: indptr int64, indices int32, val (matrix dtype), val32 (fp32 copy).
+
+    Quacks like the scipy matrices StringGrouper._get_tf_idf_matrices returns
+    (/root/reference/string_grouper/string_grouper.py:685-697): `.shape`,
+    `.toarray()`, `.indptr` ... are served from a lazily materialised scipy
+    copy, so reference-style tests and user code keep working.
+    """
+
+    def __init__(self, shape, indptr, indices, val, val32, nnz, dtype, norm_bound=1.0):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.d_indptr, self.d_indices, self.d_val, self.d_val32 = indptr, indices, val, val32
+        self.nnz = int(nnz)
+        self.dtype = np.dtype(dtype)
+        self.norm_bound = float(norm_bound)
+        self._host = None
+        self._postings = {}
+
+    @property
+    def device(self):
+        return self.d_indptr.device
+
+    @classmethod
+    def from_scipy(cls, m, device=None):
+        t = require_cuda()
+        from scipy.sparse import issparse
+        if not issparse(m):
+            raise TypeError("expected a scipy sparse matrix, got %r" % type(m))
+        m = m.tocsr()
+        if not m.has_sorted_indices:
+            m = m.sorted_indices()
+        if m.nnz >= 2**31 - 1:
+            raise OverflowError("matrix has %d stored values; int32 indices overflow" % m.nnz)
+        dtype = np.float32 if m.dtype == np.float32 else np.float64
+        device = device or t.device("cuda", t.cuda.current_device())
+        data = np.ascontiguousarray(m.data, dtype=dtype)
+        indptr = t.from_numpy(np.ascontiguousarray(m.indptr, dtype=np.int64)).to(device)
+        indices = t.from_numpy(np.ascontiguousarray(m.indices, dtype=np.int32)).to(device)
+        val = t.from_numpy(data).to(device)
+        val32 = val if dtype == np.float32 else val.to(t.float32)
+        bound = float(np.sqrt(m.multiply(m).sum(axis=1).max())) if m.nnz else 1.0
+        out = cls(m.shape, indptr, indices, val, val32, m.nnz, dtype, max(bound, 1e-30))
+        out._host = m
+        return out
+
+    def to_scipy(self):
+        if self._host is None:
+            from scipy.sparse import csr_matrix
+            n = self.nnz
+            indptr = self.d_indptr.cpu().numpy()
+            idx_dtype = np.int32 if max(self.shape) < 2**31 and n < 2**31 else np.int64
+            self._host = csr_matrix((self.d_val[:n].cpu().numpy(), self.d_indices[:n].cpu().numpy().astype(idx_dtype),
+                                     indptr.astype(idx_dtype)), shape=self.shape)
+        return self._host
+
+    def get_shape(self):
+        return self.shape
+
+    def toarray(self):
+        return self.to_scipy().toarray()
+
+    def __getattr__(self, name):
+        # anything else scipy offers (indptr, data, T, multiply, ...) comes from the host copy
+        if name.startswith("_") or name.startswith("d_"):
+            raise AttributeError(name)
+        return getattr(self.to_scipy(), name)
+
+    def postings(self, tile_w):
+        """(bucket_ptr, postings, T) of this matrix as the RIGHT operand, built once per tile width."""
+        if tile_w not in self._postings:
+            self._postings[tile_w] = build_postings(self, tile_w)
+        return self._postings[tile_w]
+
+
+def as_device_csr(m):
+    return m if isinstance(m, DeviceCSR) else DeviceCSR.from_scipy(m)
+
+
+def build_postings(B, tile_w):
+    t = require_cuda()
+    L = _lib.load()
+    n_rows, n_cols = B.shape
+    T = int(L.sg_num_tiles(n_rows, tile_w))
+    nb = n_cols * T + 1
+    if nb >= 2**31 - 1:
+        raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
+    bucket_ptr = _empty(nb, t.int32, B.device)
+    post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
+    ws_bytes = int(L.sg_postings_workspace_bytes(n_cols, T))
+    ws = _empty(ws_bytes, t.uint8, B.device)
+    _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
+                                   tile_w, _ptr(bucket_ptr), _ptr(post), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["postings"] += 2
+    return bucket_ptr, post, T
+
+
+class DeviceMatches:
+    """Result of the top-n product in HBM: COO triples ordered by (row asc, score desc)
+    or, after symmetrize(), by (row asc, col asc).  Lazily materialises the scipy CSR that
+    StringGrouper._build_matches returns in the reference (string_grouper.py:709-752)."""
+
+    def __init__(self, shape, row, col, score, nnz, max_row, out_dtype=np.float64, indptr=None):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.d_row, self.d_col, self.d_score, self.d_indptr = row, col, score, indptr
+        self.nnz = int(nnz)
+        self.max_row = int(max_row)
+        self.out_dtype = np.dtype(out_dtype)
+        self._host = None
+
+    def host_triples(self):
+        n = self.nnz
+        return (self.d_row[:n].cpu().numpy(), self.d_col[:n].cpu().numpy(), self.d_score[:n].cpu().numpy())
+
+    def to_scipy(self):
+        if self._host is None:
+            from scipy.sparse import csr_matrix
+            r, c, s = self.host_triples()
+            indptr = np.zeros(self.shape[0] + 1, dtype=np.int64)
+            np.cumsum(np.bincount(r, minlength=self.shape[0]), out=indptr[1:])
+            idx_dtype = np.int32 if max(self.shape) < 2**31 and self.nnz < 2**31 else np.int64
+            self._host = csr_matrix((s.astype(self.out_dtype, copy=False), c.astype(idx_dtype),
+                                     indptr.astype(idx_dtype)), shape=self.shape)
+        return self._host
+
+    def get_shape(self):
+        return self.shape
+
+    def toarray(self):
+        return self.to_scipy().toarray()
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name.startswith("d_"):
+            raise AttributeError(name)
+        return getattr(self.to_scipy(), name)
+
+
+def pick_tile(n_right, tile_w=None, warps=None):
+    tile_w = int(tile_w or DEFAULT_TILE_W)
+    warps = int(warps or DEFAULT_WARPS)
+    need = ((max(int(n_right), 1) + 127) // 128) * 128
+    return min(tile_w, need), warps
+
+
+def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None):
+    """C[i,:] = top_n{ j : A_i . B_j > threshold } for rows [row_begin,row_end) of A.
+
+    Device counterpart of the whole block loop of StringGrouper._build_matches
+    (string_grouper.py:734-750).  Returns DeviceMatches with absolute row ids.
+    """
+    t = require_cuda()
+    L = _lib.load()
+    if A.shape[1] != B.shape[1]:
+        raise ValueError("dimension mismatch: left has %d features, right has %d" % (A.shape[1], B.shape[1]))
+    if A.dtype != B.dtype:
+        raise TypeError("left and right matrices must have the same dtype")
+    n_left, n_right = A.shape[0], B.shape[0]
+    row_end = n_left if row_end is None else int(row_end)
+    row_begin = int(row_begin)
+    n_rows = max(row_end - row_begin, 0)
+    dev = A.device
+    top_n = int(min(int(top_n), n_right))
+    dt = _lib.SG_DTYPE_F32 if A.dtype == np.float32 else _lib.SG_DTYPE_F64
+    shape = (n_left, n_right)
+    if n_rows == 0 or n_right == 0 or top_n <= 0 or A.nnz == 0 or B.nnz == 0:
+        z32 = _empty(1, t.int32, dev)
+        return DeviceMatches(shape, z32, z32, _empty(1, t.float64, dev), 0, 0)
+
+    tile_w, warps = pick_tile(n_right, tile_w, warps)
+    bucket_ptr, post, T = B.postings(tile_w)
+    scale = A.norm_bound * B.norm_bound
+    thr_c = max(float(threshold) - CAND_MARGIN * max(scale, 1.0), 0.0)
+
+    counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] row_queue (int32 view)
+    cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or (16 * n_rows + (1 << 20))
+    for attempt in range(3):
+        cand_row = _empty(cap, t.int32, dev)
+        cand_col = _empty(cap, t.int32, dev)
+        counters.zero_()
+        _lib.check(L.sg_cossim_candidates(
+            _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
+            _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, _ptr(cand_row), _ptr(cand_col), cap,
+            ctypes.c_void_p(counters.data_ptr()), ctypes.c_void_p(counters.data_ptr() + 8), warps, _stream()))
+        LAUNCH_COUNTS["candidates"] += 1
+        n_cand = int(counters[0].item())
+        if n_cand <= cap:
+            break
+        if n_cand * 24 > 64 * 2**30:
+            raise OverflowError("%d candidate pairs above the threshold do not fit the candidate buffer; "
+                                "raise min_similarity or split the input" % n_cand)
+        cap = n_cand
+    else:
+        raise OverflowError("candidate buffer overflow")
+    if stats is not None:
+        stats["n_candidates"] = n_cand
+        stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
+
+    score = _empty(n_cand, t.float64, dev)
+    _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
+                            _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
+                            _stream()))
+    LAUNCH_COUNTS["rescore"] += 1
+
+    out_indptr = _empty(n_rows + 1, t.int64, dev)
+    out_row = _empty(n_cand, t.int32, dev)
+    out_col = _empty(n_cand, t.int32, dev)
+    out_score = _empty(n_cand, t.float64, dev)
+    tail = t.zeros(2, dtype=t.int64, device=dev)            # [0] out_nnz, [1] max_row (int32 view)
+    ws_bytes = int(L.sg_topn_select_workspace_bytes(n_cand, n_rows))
+    ws = _empty(ws_bytes, t.uint8, dev)
+    _lib.check(L.sg_topn_select(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(score), row_begin, n_rows, top_n,
+                                float(threshold), _ptr(out_indptr), _ptr(out_row), _ptr(out_col), _ptr(out_score),
+                                ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
+                                ws_bytes, _stream()))
+    LAUNCH_COUNTS["select"] += 6
+    th = tail.cpu().numpy()
+    nnz = int(th[0])
+    max_row = int(th[1:2].view(np.int32)[0])
+    return DeviceMatches(shape, out_row, out_col, out_score, nnz, max_row, indptr=out_indptr)
+
+
+def symmetrize(M):
+    """diag := 1, pattern := pattern U pattern^T, rows ordered by column
+    (string_grouper.py:419-427, :955-964) on the device."""
+    t = require_cuda()
+    L = _lib.load()
+    n = M.shape[0]
+    dev = M.d_row.device
+    cap = 2 * M.nnz + n
+    out_row = _empty(cap, t.int32, dev)
+    out_col = _empty(cap, t.int32, dev)
+    out_score = _empty(cap, t.float64, dev)
+    out_nnz = t.zeros(1, dtype=t.int64, device=dev)
+    ws_bytes = int(L.sg_symmetrize_workspace_bytes(M.nnz, n))
+    ws = _empty(ws_bytes, t.uint8, dev)
+    _lib.check(L.sg_symmetrize(n, M.nnz, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), _ptr(out_row),
+                               _ptr(out_col), _ptr(out_score), _ptr(out_nnz), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["symmetrize"] += 5
+    nnz = int(out_nnz.item())
+    return DeviceMatches(M.shape, out_row, out_col, out_score, nnz, M.max_row, out_dtype=M.out_dtype)
+
+
+def matches_from_scipy(m):
+    """Upload a host CSR of matches (e.g. returned by a user-supplied _build_matches)."""
+    t = require_cuda()
+    m = m.tocsr()
+    dev = t.device("cuda", t.cuda.current_device())
+    # keep CSR storage order (value-descending inside a row for the reference's product)
+    r2 = np.repeat(np.arange(m.shape[0], dtype=np.int32), np.diff(m.indptr))
+    row = t.from_numpy(r2).to(dev)
+    col = t.from_numpy(np.ascontiguousarray(m.indices, dtype=np.int32)).to(dev)
+    score = t.from_numpy(np.ascontiguousarray(m.data, dtype=np.float64)).to(dev)
+    max_row = int(np.diff(m.indptr).max()) if m.shape[0] else 0
+    if row.numel() == 0:
+        row = _empty(1, t.int32, dev)
+        col = _empty(1, t.int32, dev)
+        score = _empty(1, t.float64, dev)
+    return DeviceMatches(m.shape, row, col, score, m.nnz, max_row, out_dtype=m.dtype)
+
+
+def rowwise_dot(A, B):
+    """StringGrouper.dot (string_grouper.py:433-440): row-wise similarity of two equal-shape matrices."""
+    t = require_cuda()
+    L = _lib.load()
+    if A.shape != B.shape:
+        raise ValueError("shape mismatch")
+    out = _empty(A.shape[0], t.float64, A.device)
+    dt = _lib.SG_DTYPE_F32 if A.dtype == np.float32 else _lib.SG_DTYPE_F64
+    _lib.check(L.sg_rowwise_dot(A.shape[0], _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val), _ptr(B.d_indptr),
+                                _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(out), _stream()))
+    LAUNCH_COUNTS["rowdot"] += 1
+    return out[:A.shape[0]].cpu().numpy().astype(A.dtype, copy=False)

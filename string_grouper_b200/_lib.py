@@ -1,0 +1,90 @@
+"""ctypes binding of libsg_b200.so (the C ABI declared in include/sg_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a
+CUDA device is absent, the callers raise.  Build with
+`python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsg_b200.so")
+
+SG_OK = 0
+SG_ERR_INVALID = -1
+SG_ERR_CUDA = -2
+SG_ERR_OVERFLOW = -3
+SG_ERR_UNSUPPORTED = -4
+SG_DTYPE_F32 = 0
+SG_DTYPE_F64 = 1
+SG_FLAG_IGNORE_CASE = 1
+SG_FLAG_STRIP_DEFAULT = 2
+
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+_p = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_f32 = ctypes.c_float
+_f64 = ctypes.c_double
+_u32 = ctypes.c_uint
+
+# name -> (restype, argtypes); mirrors include/sg_b200.h one to one
+SIGNATURES = {
+    "sg_last_error": (ctypes.c_char_p, []),
+    "sg_abi_version": (_i32, []),
+    "sg_device_info": (_i32, [_p, _p, _p]),
+    "sg_tfidf_table_slots": (_i64, [_i32]),
+    "sg_tfidf_count": (_i32, [_p, _p, _i64, _i32, _u32, _p, _p, _p, _p, _p]),
+    "sg_tfidf_finalize_workspace_bytes": (_sz, [_i64, _i32]),
+    "sg_tfidf_finalize": (_i32, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_tfidf_vocab_keys": (_i32, [_p, _i32, _p, _p, _p]),
+    "sg_num_tiles": (_i64, [_i64, _i32]),
+    "sg_postings_workspace_bytes": (_sz, [_i64, _i64]),
+    "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _sz, _p]),
+    "sg_cossim_candidates": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _i32, _f32, _p, _p, _i64, _p,
+                                    _p, _i32, _p]),
+    "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
+    "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_symmetrize_workspace_bytes": (_sz, [_i64, _i64]),
+    "sg_symmetrize": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_rowwise_dot": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+}
+
+_LIB = None
+
+
+class SgB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsg_b200.so and declare every exported symbol; raises if absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise SgB200Error(
+                "libsg_b200.so is not built (%s). Run `python -c \"import __graft_entry__ as g; g.build()\"`; "
+                "there is no CPU fallback for the hot path." % SO_PATH)
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    """Translate a negative return code into the Python exception the reference would raise."""
+    if rc == SG_OK:
+        return
+    msg = load().sg_last_error()
+    msg = msg.decode("utf-8", "replace") if msg else "libsg_b200 error %d" % rc
+    if rc == SG_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == SG_ERR_OVERFLOW:
+        raise OverflowError(msg)
+    if rc == SG_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise SgB200Error(msg)

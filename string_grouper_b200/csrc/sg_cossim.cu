@@ -1,0 +1,544 @@
+// K2 — blocked CSR x CSR^T, thresholded, top-n per left row, for sm_100a.
+//
+// Replaces StringGrouper._build_matches
+// (/root/reference/string_grouper/string_grouper.py:709-752): the per block
+// pair sp_matmul_topn products (:737-743), the zip over right blocks (:746)
+// and the vstack over left blocks (:750).  See DESIGN.md §K2 for the layout.
+//
+//   postings_build   right matrix  -> (feature, column-tile) bucketed postings
+//   candidates       Gustavson row-wise product, fp32, shared-memory accumulator
+//                    tile per warp, emits (row, col) with score > thr - margin
+//   rescore          exact sorted-merge dot product of every candidate pair
+//   topn_select      strict threshold, top-n per row, value-descending
+#include <cub/cub.cuh>
+
+#include "sg_common.cuh"
+
+namespace sg {
+
+// ---------------------------------------------------------------------------
+// postings build
+// ---------------------------------------------------------------------------
+__global__ void postings_hist_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
+                                     const int32_t *__restrict__ indices, int tile_w, int64_t T,
+                                     int32_t *__restrict__ cnt) {
+    // one warp per right row: lanes stride over the row's entries
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t t = row / tile_w;
+    const int64_t p1 = indptr[row + 1];
+    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32)
+        atomicAdd(&cnt[(int64_t)indices[p] * T + t], 1);
+}
+
+__global__ void postings_scatter_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
+                                        const int32_t *__restrict__ indices,
+                                        const float *__restrict__ val, int tile_w, int64_t T,
+                                        int32_t *__restrict__ cursor, uint2 *__restrict__ post) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t t = row / tile_w;
+    const int64_t p1 = indptr[row + 1];
+    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32) {
+        const int32_t pos = atomicAdd(&cursor[(int64_t)indices[p] * T + t], 1);
+        post[pos] = make_uint2((uint32_t)row, __float_as_uint(val[p]));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// candidate generation
+// ---------------------------------------------------------------------------
+constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-privately
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
+                         const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
+                         int64_t n_right, const int32_t *__restrict__ bptr,
+                         const uint2 *__restrict__ post, int W, int64_t T, float thr_c,
+                         int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
+                         unsigned long long cap, unsigned long long *__restrict__ cand_count,
+                         int32_t *__restrict__ row_queue) {
+    extern __shared__ __align__(16) float smem_acc[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *acc = smem_acc + (size_t)warp * W;
+
+    for (int c = lane * 4; c < W; c += 128) *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    for (;;) {
+        int64_t row = 0;
+        if (lane == 0) row = row_begin + atomicAdd(row_queue, 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= row_end) break;
+        const int64_t p0 = a_indptr[row];
+        const int nf = (int)(a_indptr[row + 1] - p0);
+        if (nf == 0) continue;
+
+        for (int64_t t = 0; t < T; ++t) {
+            const int c0 = (int)(t * W);
+            for (int base = 0; base < nf; base += 32) {
+                const int k = base + lane;
+                int b0 = 0, b1 = 0;
+                float a = 0.f;
+                if (k < nf) {
+                    const int64_t f = a_idx[p0 + k];
+                    a = a_val[p0 + k];
+                    const int32_t *bp = bptr + f * T + t;
+                    b0 = bp[0];
+                    b1 = bp[1];
+                }
+                const int len = b1 - b0;
+                // short buckets: every lane walks its own bucket (one L2 latency for all of them);
+                // two lanes may meet on one column, hence the shared-memory atomic.
+                if (len > 0 && len <= SHORT_BUCKET) {
+                    for (int j = 0; j < len; ++j) {
+                        const uint2 e = post[b0 + j];
+                        atomicAdd(acc + ((int)e.x - c0), a * __uint_as_float(e.y));
+                    }
+                }
+                __syncwarp();
+                // long buckets: the whole warp streams one bucket; columns inside one posting
+                // list are distinct, so the read-modify-write needs no atomics.
+                unsigned m = __ballot_sync(FULL, len > SHORT_BUCKET);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int s = __shfl_sync(FULL, b0, src);
+                    const int e = __shfl_sync(FULL, b1, src);
+                    const float ak = __shfl_sync(FULL, a, src);
+                    int p = s + lane;
+                    for (; p + 96 < e; p += 128) {
+                        const uint2 e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
+                        acc[(int)e0.x - c0] += ak * __uint_as_float(e0.y);
+                        acc[(int)e1.x - c0] += ak * __uint_as_float(e1.y);
+                        acc[(int)e2.x - c0] += ak * __uint_as_float(e2.y);
+                        acc[(int)e3.x - c0] += ak * __uint_as_float(e3.y);
+                    }
+                    for (; p < e; p += 32) {
+                        const uint2 e0 = post[p];
+                        acc[(int)e0.x - c0] += ak * __uint_as_float(e0.y);
+                    }
+                    __syncwarp();
+                }
+            }
+            // sweep: report scores above the candidate threshold, clear the tile
+            for (int c = lane * 4; c < W; c += 128) {
+                float4 *q = reinterpret_cast<float4 *>(acc + c);
+                const float4 v = *q;
+                const unsigned nz = (__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) |
+                                     __float_as_uint(v.w)) << 1;
+                if (nz) {
+                    *q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    if (mx > thr_c) {
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (vv[i] > thr_c) {
+                                const unsigned long long slot = atomicAdd(cand_count, 1ull);
+                                if (slot < cap) {
+                                    cand_row[slot] = (int32_t)row;
+                                    cand_col[slot] = c0 + c + i;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// exact re-scoring
+// ---------------------------------------------------------------------------
+template <typename T>
+struct ExactOps;
+template <>
+struct ExactOps<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+template <>
+struct ExactOps<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+
+template <typename T>
+__device__ __forceinline__ T merge_dot(const int32_t *__restrict__ ai, const T *__restrict__ av, int64_t pa,
+                                       int64_t ea, const int32_t *__restrict__ bi,
+                                       const T *__restrict__ bv, int64_t pb, int64_t eb) {
+    T sum = (T)0;
+    if (pa >= ea || pb >= eb) return sum;
+    int32_t fa = ai[pa], fb = bi[pb];
+    for (;;) {
+        if (fa == fb) {
+            sum = ExactOps<T>::add(sum, ExactOps<T>::mul(av[pa], bv[pb]));
+            ++pa;
+            ++pb;
+            if (pa >= ea || pb >= eb) break;
+            fa = ai[pa];
+            fb = bi[pb];
+        } else if (fa < fb) {
+            if (++pa >= ea) break;
+            fa = ai[pa];
+        } else {
+            if (++pb >= eb) break;
+            fb = bi[pb];
+        }
+    }
+    return sum;
+}
+
+template <typename T>
+__global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
+                               const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
+                               const T *__restrict__ a_val, const int64_t *__restrict__ b_indptr,
+                               const int32_t *__restrict__ b_idx, const T *__restrict__ b_val,
+                               double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = cr[i], c = cc[i];
+    out[i] = (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+                                  b_indptr[c + 1]);
+}
+
+template <typename T>
+__global__ void rowwise_dot_kernel(int64_t n, const int64_t *__restrict__ a_indptr,
+                                   const int32_t *__restrict__ a_idx, const T *__restrict__ a_val,
+                                   const int64_t *__restrict__ b_indptr, const int32_t *__restrict__ b_idx,
+                                   const T *__restrict__ b_val, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (double)merge_dot<T>(a_idx, a_val, a_indptr[i], a_indptr[i + 1], b_idx, b_val, b_indptr[i],
+                                  b_indptr[i + 1]);
+}
+
+// ---------------------------------------------------------------------------
+// top-n selection
+// ---------------------------------------------------------------------------
+__global__ void select_keys_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
+                                   int64_t row_begin, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = ((uint64_t)(uint32_t)(cr[i] - (int32_t)row_begin) << 32) | (uint32_t)cc[i];
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void select_segments_kernel(int64_t n, const uint64_t *__restrict__ keys, int64_t n_rows,
+                                       int64_t *__restrict__ seg) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    const uint64_t want = (uint64_t)r << 32;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    seg[r] = lo;
+}
+
+// better(x, y): x ranks before y  (score desc, then position asc == column asc)
+__device__ __forceinline__ bool ranks_before(double sx, int64_t px, double sy, int64_t py) {
+    return sx > sy || (sx == sy && px < py);
+}
+
+__global__ void select_count_kernel(int64_t n_rows, const int64_t *__restrict__ seg,
+                                    const uint32_t *__restrict__ vals, const double *__restrict__ score,
+                                    double thr, int top_n, int64_t *__restrict__ out_cnt,
+                                    int32_t *__restrict__ out_max) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int64_t s = seg[r], e = seg[r + 1];
+    int c = 0;
+    for (int64_t p = s + lane_id(); p < e; p += 32) c += score[vals[p]] > thr ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane_id() == 0) {
+        const int k = c < top_n ? c : top_n;
+        out_cnt[r] = k;
+        if (k > 0) atomicMax(out_max, k);
+    }
+}
+
+__global__ void select_write_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restrict__ seg,
+                                    const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                    const double *__restrict__ score, double thr, int top_n,
+                                    const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_row,
+                                    int32_t *__restrict__ out_col, double *__restrict__ out_score) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int64_t s = seg[r], e = seg[r + 1];
+    if (s == e) return;
+    const int64_t ob = out_indptr[r];
+    const int lane = lane_id();
+    const double NEG = -1.0e300;
+    if (e - s <= 32) {
+        const int64_t p = s + lane;
+        double sc = NEG;
+        int32_t col = 0;
+        if (p < e) {
+            const double v = score[vals[p]];
+            if (v > thr) sc = v;
+            col = (int32_t)(keys[p] & 0xffffffffu);
+        }
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double sj = __shfl_sync(FULL, sc, j);
+            rank += ranks_before(sj, j, sc, lane) ? 1 : 0;
+        }
+        if (sc > NEG && rank < top_n) {
+            out_row[ob + rank] = (int32_t)(r + row_begin);
+            out_col[ob + rank] = col;
+            out_score[ob + rank] = sc;
+        }
+        return;
+    }
+    // long rows (clusters of near-identical strings): rank by counting, O(m^2 / 32) per row
+    for (int64_t p = s + lane; p < e; p += 32) {
+        const double sc = score[vals[p]];
+        if (!(sc > thr)) continue;
+        int64_t rank = 0;
+        for (int64_t q = s; q < e && rank < top_n; ++q) {
+            const double sq = score[vals[q]];
+            rank += (sq > thr && ranks_before(sq, q, sc, p)) ? 1 : 0;
+        }
+        if (rank < top_n) {
+            out_row[ob + rank] = (int32_t)(r + row_begin);
+            out_col[ob + rank] = (int32_t)(keys[p] & 0xffffffffu);
+            out_score[ob + rank] = sc;
+        }
+    }
+}
+
+__global__ void select_finish_kernel(int64_t n_rows, const int64_t *__restrict__ out_indptr,
+                                     int64_t *__restrict__ out_nnz) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out_nnz = out_indptr[n_rows];
+}
+
+static int bits_for(uint64_t v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b < 1 ? 1 : b;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int64_t sg_num_tiles(int64_t n_right, int tile_w) {
+    if (tile_w <= 0) return 0;
+    const int64_t t = (n_right + tile_w - 1) / tile_w;
+    return t < 1 ? 1 : t;
+}
+
+size_t sg_postings_workspace_bytes(int64_t n_cols, int64_t n_tiles) {
+    const size_t nb = (size_t)n_cols * (size_t)n_tiles + 1;
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (int32_t *)nullptr, (int64_t)nb);
+    return align_up(nb * sizeof(int32_t), 256) + align_up(cub_bytes, 256) + 1024;
+}
+
+int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr,
+                      const int32_t *indices, const float *val32, int tile_w, int32_t *bucket_ptr,
+                      void *postings, void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (tile_w <= 0 || (tile_w & 127)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 128");
+    if (nnz >= (int64_t)0x7fffffff) return fail(SG_ERR_OVERFLOW, "right matrix nnz %lld does not fit int32 postings", (long long)nnz);
+    const int64_t T = sg_num_tiles(n_rows, tile_w);
+    const int64_t nb = n_cols * T + 1;
+    if (nb >= (int64_t)0x7fffffff) return fail(SG_ERR_OVERFLOW, "bucket table %lld too large", (long long)nb);
+    Arena ar(ws, ws_bytes);
+    int32_t *cursor = ar.take<int32_t>((size_t)nb);
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (int32_t *)nullptr, nb);
+    char *cub_tmp = ar.take<char>(cub_bytes);
+    if (!ar.ok()) return fail(SG_ERR_INVALID, "postings workspace too small (%zu < %zu)", ws_bytes, ar.off);
+
+    SG_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(int32_t), st));
+    if (n_rows > 0) {
+        const int wpb = 8;
+        const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
+        postings_hist_kernel<<<grid, wpb * 32, 0, st>>>(n_rows, indptr, indices, tile_w, T, cursor);
+        SG_LAUNCH_CHECK();
+    }
+    SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursor, bucket_ptr, nb, st));
+    SG_CUDA_TRY(cudaMemcpyAsync(cursor, bucket_ptr, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (n_rows > 0) {
+        const int wpb = 8;
+        const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
+        postings_scatter_kernel<<<grid, wpb * 32, 0, st>>>(n_rows, indptr, indices, val32, tile_w, T, cursor,
+                                                           (uint2 *)postings);
+        SG_LAUNCH_CHECK();
+    }
+    return SG_OK;
+}
+
+}  // extern "C"
+
+template <int NW>
+static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
+                             int64_t row_begin, int64_t row_end, int64_t n_right,
+                             const int32_t *bucket_ptr, const void *postings, int tile_w, float thr_c,
+                             int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
+                             unsigned long long *cand_count, int32_t *row_queue, int n_sm, cudaStream_t st) {
+    const size_t smem = (size_t)NW * tile_w * sizeof(float);
+    SG_CUDA_TRY(cudaFuncSetAttribute(cossim_candidates_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t T = sg_num_tiles(n_right, tile_w);
+    const int64_t n_rows = row_end - row_begin;
+    int64_t ctas = (n_rows + NW - 1) / NW;
+    if (ctas > n_sm) ctas = n_sm;
+    if (ctas < 1) ctas = 1;
+    cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
+        a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr, (const uint2 *)postings, tile_w, T,
+        thr_c, cand_row, cand_col, (unsigned long long)cand_cap, cand_count, row_queue);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+extern "C" {
+
+int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
+                         int64_t row_begin, int64_t row_end, int64_t n_right, int64_t n_cols,
+                         const int32_t *bucket_ptr, const void *postings, int tile_w, float cand_threshold,
+                         int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
+                         unsigned long long *cand_count, int32_t *row_queue, int warps_per_cta,
+                         void *stream_) {
+    (void)n_cols;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (row_end <= row_begin || n_right <= 0) return SG_OK;
+    if (tile_w <= 0 || (tile_w & 127)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 128");
+    if (!(cand_threshold >= 0.f)) return fail(SG_ERR_INVALID, "cand_threshold must be >= 0");
+    int dev = 0, n_sm = 0, smem_optin = 0;
+    SG_CUDA_TRY(cudaGetDevice(&dev));
+    SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    SG_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if ((size_t)warps_per_cta * tile_w * sizeof(float) > (size_t)smem_optin)
+        return fail(SG_ERR_INVALID, "warps_per_cta*tile_w*4 = %zu exceeds %d bytes of shared memory",
+                    (size_t)warps_per_cta * tile_w * sizeof(float), smem_optin);
+#define SG_CASE(NW)                                                                                          \
+    case NW:                                                                                                 \
+        return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr,  \
+                                     postings, tile_w, cand_threshold, cand_row, cand_col, cand_cap,         \
+                                     cand_count, row_queue, n_sm, st);
+    switch (warps_per_cta) {
+        SG_CASE(4)
+        SG_CASE(8)
+        SG_CASE(16)
+        SG_CASE(24)
+        SG_CASE(32)
+        default:
+            return fail(SG_ERR_INVALID, "warps_per_cta must be one of 4, 8, 16, 24, 32");
+    }
+#undef SG_CASE
+}
+
+int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const int64_t *a_indptr,
+               const int32_t *a_indices, const void *a_val, const int64_t *b_indptr, const int32_t *b_indices,
+               const void *b_val, int dtype, double *score_out, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_cand <= 0) return SG_OK;
+    const unsigned grid = (unsigned)((n_cand + 255) / 256);
+    if (dtype == SG_DTYPE_F64)
+        rescore_kernel<double><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
+                                                     (const double *)a_val, b_indptr, b_indices,
+                                                     (const double *)b_val, score_out);
+    else if (dtype == SG_DTYPE_F32)
+        rescore_kernel<float><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
+                                                    (const float *)a_val, b_indptr, b_indices,
+                                                    (const float *)b_val, score_out);
+    else
+        return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+int sg_rowwise_dot(int64_t n_rows, const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
+                   const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype, double *out,
+                   void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_rows <= 0) return SG_OK;
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    if (dtype == SG_DTYPE_F64)
+        rowwise_dot_kernel<double><<<grid, 256, 0, st>>>(n_rows, a_indptr, a_indices, (const double *)a_val,
+                                                         b_indptr, b_indices, (const double *)b_val, out);
+    else if (dtype == SG_DTYPE_F32)
+        rowwise_dot_kernel<float><<<grid, 256, 0, st>>>(n_rows, a_indptr, a_indices, (const float *)a_val,
+                                                        b_indptr, b_indices, (const float *)b_val, out);
+    else
+        return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+size_t sg_topn_select_workspace_bytes(int64_t n_cand, int64_t n_rows) {
+    size_t sort_bytes = 0, scan_bytes = 0;
+    const int64_t n = n_cand < 1 ? 1 : n_cand;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, n);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int64_t *)nullptr, (int64_t *)nullptr, n_rows + 1);
+    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) +
+           2 * align_up((size_t)(n_rows + 2) * 8, 256) + align_up(sort_bytes, 256) + align_up(scan_bytes, 256) + 4096;
+}
+
+int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const double *score,
+                   int64_t row_begin, int64_t n_rows, int top_n, double threshold, int64_t *out_indptr,
+                   int32_t *out_row, int32_t *out_col, double *out_score, int64_t *out_nnz,
+                   int32_t *out_max_row, void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_rows < 0 || n_cand < 0) return fail(SG_ERR_INVALID, "negative size");
+    SG_CUDA_TRY(cudaMemsetAsync(out_max_row, 0, sizeof(int32_t), st));
+    if (n_cand == 0 || top_n <= 0) {
+        SG_CUDA_TRY(cudaMemsetAsync(out_indptr, 0, (size_t)(n_rows + 1) * sizeof(int64_t), st));
+        SG_CUDA_TRY(cudaMemsetAsync(out_nnz, 0, sizeof(int64_t), st));
+        return SG_OK;
+    }
+    Arena ar(ws, ws_bytes);
+    uint64_t *keys_in = ar.take<uint64_t>((size_t)n_cand);
+    uint64_t *keys = ar.take<uint64_t>((size_t)n_cand);
+    uint32_t *vals_in = ar.take<uint32_t>((size_t)n_cand);
+    uint32_t *vals = ar.take<uint32_t>((size_t)n_cand);
+    int64_t *seg = ar.take<int64_t>((size_t)n_rows + 2);
+    int64_t *cnt = ar.take<int64_t>((size_t)n_rows + 2);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, keys, vals_in, vals, n_cand);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, out_indptr, n_rows + 1);
+    char *sort_tmp = ar.take<char>(sort_bytes);
+    char *scan_tmp = ar.take<char>(scan_bytes);
+    if (!ar.ok()) return fail(SG_ERR_INVALID, "select workspace too small (%zu < %zu)", ws_bytes, ar.off);
+
+    const unsigned g1 = (unsigned)((n_cand + 255) / 256);
+    select_keys_kernel<<<g1, 256, 0, st>>>(n_cand, cand_row, cand_col, row_begin, keys_in, vals_in);
+    SG_LAUNCH_CHECK();
+    const int end_bit = 32 + bits_for((uint64_t)(n_rows > 0 ? n_rows - 1 : 0));
+    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys, vals_in, vals, n_cand, 0,
+                                                end_bit > 64 ? 64 : end_bit, st));
+    const unsigned g2 = (unsigned)((n_rows + 1 + 255) / 256);
+    select_segments_kernel<<<g2, 256, 0, st>>>(n_cand, keys, n_rows, seg);
+    SG_LAUNCH_CHECK();
+    SG_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(n_rows + 2) * sizeof(int64_t), st));
+    const int wpb = 8;
+    const unsigned g3 = (unsigned)((n_rows + wpb - 1) / wpb);
+    if (n_rows > 0) {
+        select_count_kernel<<<g3, wpb * 32, 0, st>>>(n_rows, seg, vals, score, threshold, top_n, cnt, out_max_row);
+        SG_LAUNCH_CHECK();
+    }
+    SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cnt, out_indptr, n_rows + 1, st));
+    if (n_rows > 0) {
+        select_write_kernel<<<g3, wpb * 32, 0, st>>>(n_rows, row_begin, seg, keys, vals, score, threshold, top_n,
+                                                     out_indptr, out_row, out_col, out_score);
+        SG_LAUNCH_CHECK();
+    }
+    select_finish_kernel<<<1, 32, 0, st>>>(n_rows, out_indptr, out_nnz);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""-m gpu: K2 (postings -> candidates -> exact re-score -> top-n select) and K4 (symmetrise)
+through the C ABI, against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from parity import compare_triples, csr_triples, row_cutoffs
+from synth_corpus import make_names
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import pipeline
+    return pipeline
+
+
+def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None):
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    m, d, _ = P.tf_idf_matrices(master, dupes, dtype=dtype)
+    ref = P.build_matches(m, d, None, top_n, thr, n_threads=4)
+    A = D.DeviceCSR.from_scipy(m)
+    B = A if dupes is None else D.DeviceCSR.from_scipy(d)
+    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps)
+    return m, d, ref, got
+
+
+@pytest.mark.parametrize("n,top_n,thr,dtype", [
+    (2000, 20, 0.8, np.float64),
+    (2000, 20, 0.8, np.float32),
+    (5000, 5, 0.6, np.float64),
+    (3000, 1, 0.5, np.float64),
+    (20000, 20, 0.8, np.float64),
+])
+def test_self_match_matches_oracle(n, top_n, thr, dtype):
+    names = make_names(n, seed=1)
+    m, d, ref, got = _run(names, None, top_n, thr, dtype)
+    gr, gc, gs = got.host_triples()
+    cut = row_cutoffs(ref.indptr, ref.data, top_n, n)
+    st = compare_triples(csr_triples(ref), (gr, gc, gs), n, thr, cutoff_row=cut, label="self %d" % n)
+    assert st["common"] > n * 0.9          # at least the diagonal
+    assert got.max_row == int(np.diff(ref.indptr).max())
+    # entries of a row come out by descending score (sort=True, string_grouper.py:730)
+    same_row = gr[1:] == gr[:-1]
+    assert np.all(gs[1:][same_row] <= gs[:-1][same_row])
+    assert np.all(np.diff(gr) >= 0)
+
+
+def test_two_series_and_tilings_agree():
+    master = make_names(3000, seed=2)
+    dupes = make_names(1500, seed=2)[:1000] + make_names(500, seed=3)
+    m, d, ref, got = _run(master, dupes, 20, 0.7)
+    cut = row_cutoffs(ref.indptr, ref.data, 20, len(master))
+    compare_triples(csr_triples(ref), got.host_triples(), len(dupes), 0.7, cutoff_row=cut, label="two-series")
+    # block invariance (reference tests test_n_blocks_*): any tile shape gives the same answer
+    for tile_w, warps in [(128, 4), (256, 8), (1024, 16), (3072, 16), (1536, 32)]:
+        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps)
+        a, b = got.host_triples(), g2.host_triples()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_top_n_larger_than_right_and_empty_rows():
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    master = ["ab", "foo inc", "foo inc.", "", "bar llc", "x", "foo incorporated", "bar l.l.c"]
+    m, d, _ = P.tf_idf_matrices(master)
+    ref = P.build_matches(m, d, None, 50, 0.1)
+    A = D.DeviceCSR.from_scipy(m)
+    got = D.cossim_topn(A, A, 50, 0.1)
+    compare_triples(csr_triples(ref), got.host_triples(), len(master), 0.1, label="tiny")
+    np.testing.assert_allclose(got.toarray(), ref.toarray(), atol=1e-12)
+
+
+def test_reference_fixture_build_matches():
+    """test_build_matches (reference test_string_grouper.py:546-556): exact dense answer."""
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    m, d, _ = P.tf_idf_matrices(['foo', 'bar', 'baz'], ['foo', 'bar', 'bop'])
+    got = D.cossim_topn(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(d), 20, 0.8)
+    np.testing.assert_array_equal(got.toarray(), np.array([[1., 0., 0.], [0., 1., 0.], [0., 0., 0.]]))
+
+
+def test_symmetrize_matches_lil_restatement():
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    names = make_names(4000, seed=5) + ["zz", ""]
+    m, d, ref, got = _run(names, None, 3, 0.75)
+    ref_sym = P.fix_diagonal_and_symmetrize(ref)
+    sym = D.symmetrize(got)
+    r, c, s = sym.host_triples()
+    n = len(names)
+    cut = row_cutoffs(ref.indptr, ref.data, 3, n)
+    compare_triples(csr_triples(ref_sym), (r, c, s), n, 0.75, cutoff_row=cut, cutoff_col=cut, label="symm")
+    key = r.astype(np.int64) * n + c
+    assert np.all(np.diff(key) > 0)                      # (row, col) ascending, no duplicates
+    assert np.all(s[r == c] == 1.0) and (r == c).sum() == n
+
+
+def test_rowwise_dot():
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    a = make_names(1000, seed=7)
+    b = make_names(1000, seed=7)[:500] + make_names(500, seed=8)
+    m, d, _ = P.tf_idf_matrices(a, b)
+    ref = np.asarray(m.multiply(d).sum(axis=1)).squeeze(axis=1)
+    got = D.rowwise_dot(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(d))
+    np.testing.assert_allclose(got, ref, atol=1e-12)
