@@ -53,43 +53,46 @@ int sg_device_info(int *sm_count, int *smem_optin_bytes, int *l2_bytes);
  * bytes that are already pure ASCII (the Python host has run lower()/NFKD on
  * the rare non-ASCII rows, exactly sg.py:372-375), with n_docs+1 offsets.
  *
- * Phase 1 (sg_tfidf_count): per document: strip/fold bytes, pack n-grams into
- * order-preserving keys (7 bits per char, big endian), sort + unique + count
- * inside the warp, add 1 to df[key] per distinct key, store the (key,tf)
- * runs at the document's byte offset in `scratch_*` and the run length in
- * `row_nnz`.  `df_table` has 2^(7*ngram) int32 slots (ngram <= 4) and must be
- * zeroed by the caller.
+ * Phase 1 (sg_tfidf_count): per document (one warp): strip / fold bytes, pack
+ * n-grams into order-preserving keys (7 bits per char, big endian), sort the
+ * keys in the warp, run-length encode to (key, tf) stored at the document's
+ * byte offset in scratch_key / scratch_tf, row_nnz[doc] = number of runs,
+ * df_table[key] += 1 per run.  `df_table` has sg_tfidf_table_slots(ngram)
+ * = 2^(7*ngram) int32 slots (1 <= ngram <= 4) and must be zeroed by the
+ * caller; the four scratch arrays have total_bytes elements each
+ * (scratch_clean / scratch_sort are only touched by documents longer than 256
+ * characters).  row_nnz has n_docs + 1 slots.
  * ------------------------------------------------------------------------- */
 int64_t sg_tfidf_table_slots(int ngram);
 int sg_tfidf_count(const uint8_t *bytes /*[dev]*/, const int64_t *offsets /*[dev] n_docs+1*/,
-                   int64_t n_docs, int ngram, unsigned flags,
-                   int32_t *df_table /*[dev] slots, zeroed*/,
-                   uint32_t *scratch_key /*[dev] total_bytes*/, uint16_t *scratch_tf /*[dev] total_bytes*/,
-                   int32_t *row_nnz /*[dev] n_docs*/, void *stream);
+                   int64_t n_docs, int ngram, unsigned flags, int32_t *df_table /*[dev] slots, zeroed*/,
+                   uint8_t *scratch_clean /*[dev]*/, uint32_t *scratch_sort /*[dev]*/,
+                   uint32_t *scratch_key /*[dev]*/, uint32_t *scratch_tf /*[dev]*/,
+                   int32_t *row_nnz /*[dev] n_docs+1*/, void *stream);
 
 /*
- * Phase 2 (sg_tfidf_finalize): exclusive scan of row_nnz -> indptr (int64),
- * exclusive scan of (df>0) over the key table -> column id = rank of the
- * n-gram in sorted order (sklearn _sort_features), idf = ln((1+n)/(1+df))+1,
- * x = tf*idf, row L2 norm accumulated in double in column order, IEEE sqrt
- * and divide; writes indices + f64 values + f32 values of all n_docs rows.
- * `vocab_size` [dev] receives V.  `nnz_total` [dev] receives indptr[n_docs].
- * The caller sizes `indices/val64/val32` with total_bytes entries (an upper
- * bound of nnz), so no host read-back is needed between the phases.
+ * Phase 2 (sg_tfidf_finalize): exclusive scan of row_nnz -> indptr (int64);
+ * exclusive scan of (df > 0) over the key table -> rank_table[key] = column id
+ * = rank of the n-gram in sorted order (sklearn _sort_features);
+ * idf = ln((1+n)/(1+df)) + 1 and x = tf*idf in the matrix dtype; row L2 norm
+ * accumulated in double in column order, IEEE sqrt and divide (sklearn
+ * _inplace_csr_row_normalize_l2); writes indices, values in the matrix dtype
+ * (val64 for f64, may be NULL for f32) and an fp32 copy for K2.
+ * `vocab_size` [dev] receives V, `nnz_total` [dev] receives indptr[n_docs].
+ * The caller sizes indices/val64/val32 with total_bytes entries (an upper
+ * bound of nnz), so no host read-back is needed between the two phases.
  */
 size_t sg_tfidf_finalize_workspace_bytes(int64_t n_docs, int ngram);
 int sg_tfidf_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs, int ngram, int dtype,
-                      int32_t *df_table /*[dev] in: df, out: rank (column id)*/,
-                      const uint32_t *scratch_key, const uint16_t *scratch_tf,
-                      const int32_t *row_nnz,
+                      const int32_t *df_table /*[dev]*/, int32_t *rank_table /*[dev] slots*/,
+                      const uint32_t *scratch_key, const uint32_t *scratch_tf, int32_t *row_nnz,
                       int64_t *indptr /*[dev] n_docs+1*/, int32_t *indices /*[dev]*/,
                       double *val64 /*[dev]*/, float *val32 /*[dev]*/,
                       int32_t *vocab_size /*[dev] 1*/, int64_t *nnz_total /*[dev] 1*/,
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
-/* Sorted vocabulary keys (for get_feature_names-style inspection and tests). */
-int sg_tfidf_vocab_keys(const int32_t *df_rank_table /*[dev] after finalize*/, int ngram,
-                        const int32_t *df_raw /*[dev] copy of df before finalize, may be NULL*/,
+/* keys_out[c] = packed n-gram of column c (sorted vocabulary), V entries. */
+int sg_tfidf_vocab_keys(const int32_t *df_table /*[dev]*/, const int32_t *rank_table /*[dev]*/, int ngram,
                         uint32_t *keys_out /*[dev] V*/, void *stream);
 
 /* ------------------------------------------------------------------------- *
@@ -169,8 +172,10 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
  * output ordered by (row, col) ascending like tolil().tocsr().
  * Output capacity needed: 2*nnz_in + n.
  * ------------------------------------------------------------------------- */
+#define SG_SYMM_FIX_DIAGONAL 1 /* _fix_diagonal,     sg.py:955-958 */
+#define SG_SYMM_MIRROR 2       /* _symmetrize_matrix, sg.py:961-964 */
 size_t sg_symmetrize_workspace_bytes(int64_t nnz_in, int64_t n);
-int sg_symmetrize(int64_t n, int64_t nnz_in, const int32_t *in_row, const int32_t *in_col,
+int sg_symmetrize(int64_t n, int64_t nnz_in, int flags, const int32_t *in_row, const int32_t *in_col,
                   const double *in_score, int32_t *out_row, int32_t *out_col, double *out_score,
                   int64_t *out_nnz /*[dev] 1*/, void *ws, size_t ws_bytes, void *stream);
 

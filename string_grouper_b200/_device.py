@@ -59,9 +59,12 @@ class DeviceCSR:
     copy, so reference-style tests and user code keep working.
     """
 
-    def __init__(self, shape, indptr, indices, val, val32, nnz, dtype, norm_bound=1.0):
+    def __init__(self, shape, indptr, indices, val, val32, nnz, dtype, norm_bound=1.0, base=0):
         self.shape = (int(shape[0]), int(shape[1]))
+        # indptr holds ABSOLUTE positions into indices/val (a row-range view of a bigger matrix keeps
+        # the parent's arrays and starts at `base`); the kernels never assume indptr[0] == 0.
         self.d_indptr, self.d_indices, self.d_val, self.d_val32 = indptr, indices, val, val32
+        self.base = int(base)
         self.nnz = int(nnz)
         self.dtype = np.dtype(dtype)
         self.norm_bound = float(norm_bound)
@@ -98,10 +101,11 @@ class DeviceCSR:
     def to_scipy(self):
         if self._host is None:
             from scipy.sparse import csr_matrix
-            n = self.nnz
-            indptr = self.d_indptr.cpu().numpy()
-            idx_dtype = np.int32 if max(self.shape) < 2**31 and n < 2**31 else np.int64
-            self._host = csr_matrix((self.d_val[:n].cpu().numpy(), self.d_indices[:n].cpu().numpy().astype(idx_dtype),
+            lo, hi = self.base, self.base + self.nnz
+            indptr = self.d_indptr[:self.shape[0] + 1].cpu().numpy() - lo
+            idx_dtype = np.int32 if max(self.shape) < 2**31 and self.nnz < 2**31 else np.int64
+            self._host = csr_matrix((self.d_val[lo:hi].cpu().numpy(),
+                                     self.d_indices[lo:hi].cpu().numpy().astype(idx_dtype),
                                      indptr.astype(idx_dtype)), shape=self.shape)
         return self._host
 
@@ -158,6 +162,15 @@ class DeviceMatches:
         self.max_row = int(max_row)
         self.out_dtype = np.dtype(out_dtype)
         self._host = None
+        self.pending_fix_diagonal = False
+        self.pending_mirror = False
+
+    def with_pending(self, fix_diagonal=False, mirror=False):
+        """Record a post-processing step (StringGrouper._fix_diagonal / _symmetrize_matrix); the fused K4
+        launch happens in apply_pending()."""
+        self.pending_fix_diagonal |= bool(fix_diagonal)
+        self.pending_mirror |= bool(mirror)
+        return self
 
     def host_triples(self):
         n = self.nnz
@@ -270,13 +283,14 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     return DeviceMatches(shape, out_row, out_col, out_score, nnz, max_row, indptr=out_indptr)
 
 
-def symmetrize(M):
-    """diag := 1, pattern := pattern U pattern^T, rows ordered by column
+def symmetrize(M, fix_diagonal=True, mirror=True):
+    """diag := 1 (fix_diagonal), pattern := pattern U pattern^T (mirror), rows ordered by column
     (string_grouper.py:419-427, :955-964) on the device."""
     t = require_cuda()
     L = _lib.load()
     n = M.shape[0]
     dev = M.d_row.device
+    flags = (_lib.SG_SYMM_FIX_DIAGONAL if fix_diagonal else 0) | (_lib.SG_SYMM_MIRROR if mirror else 0)
     cap = 2 * M.nnz + n
     out_row = _empty(cap, t.int32, dev)
     out_col = _empty(cap, t.int32, dev)
@@ -284,7 +298,7 @@ def symmetrize(M):
     out_nnz = t.zeros(1, dtype=t.int64, device=dev)
     ws_bytes = int(L.sg_symmetrize_workspace_bytes(M.nnz, n))
     ws = _empty(ws_bytes, t.uint8, dev)
-    _lib.check(L.sg_symmetrize(n, M.nnz, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), _ptr(out_row),
+    _lib.check(L.sg_symmetrize(n, M.nnz, flags, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), _ptr(out_row),
                                _ptr(out_col), _ptr(out_score), _ptr(out_nnz), _ptr(ws), ws_bytes, _stream()))
     LAUNCH_COUNTS["symmetrize"] += 5
     nnz = int(out_nnz.item())
@@ -321,3 +335,88 @@ def rowwise_dot(A, B):
                                 _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(out), _stream()))
     LAUNCH_COUNTS["rowdot"] += 1
     return out[:A.shape[0]].cpu().numpy().astype(A.dtype, copy=False)
+
+
+class DeviceVocabulary:
+    """df / rank tables of the fitted vectoriser (the device twin of TfidfVectorizer.vocabulary_ / idf_)."""
+
+    def __init__(self, df_table, rank_table, ngram, n_docs, vocab_size):
+        self.d_df, self.d_rank = df_table, rank_table
+        self.ngram, self.n_docs, self.size = int(ngram), int(n_docs), int(vocab_size)
+
+    def feature_names(self):
+        """Sorted n-grams, column order of the TF-IDF matrices (sklearn get_feature_names_out)."""
+        from ._ingest import decode_vocab_keys
+        t = require_cuda()
+        L = _lib.load()
+        keys = _empty(self.size, t.int32, self.d_df.device)
+        _lib.check(L.sg_tfidf_vocab_keys(_ptr(self.d_df), _ptr(self.d_rank), self.ngram, _ptr(keys), _stream()))
+        return decode_vocab_keys(keys[:self.size].cpu().numpy().view(np.uint32), self.ngram)
+
+
+def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None):
+    """K1: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM.
+
+    Device counterpart of _fit_vectorizer + transform (string_grouper.py:685-707): the vocabulary /
+    df / idf are fitted on ALL rows, then rows [0, n_master) form the master matrix and the rest the
+    duplicate matrix (views of the same device arrays).  Returns (master, duplicates | None, vocab).
+    """
+    t = require_cuda()
+    L = _lib.load()
+    device = device or t.device("cuda", t.cuda.current_device())
+    n_docs = len(offsets) - 1
+    total = int(offsets[-1])
+    slots = int(L.sg_tfidf_table_slots(int(ngram)))
+    if slots < 0:
+        raise NotImplementedError("ngram_size=%r: the device vectoriser supports 1 <= ngram_size <= 4" % (ngram,))
+    np_dtype = np.float32 if np.dtype(dtype) == np.float32 else np.float64
+    d_bytes = t.from_numpy(np.ascontiguousarray(data)).to(device, non_blocking=True) if total else _empty(1, t.uint8, device)
+    d_off = t.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
+    df = t.zeros(slots, dtype=t.int32, device=device)
+    rank = _empty(slots, t.int32, device)
+    s_clean = _empty(total, t.uint8, device)
+    s_sort = _empty(total, t.int32, device)
+    s_key = _empty(total, t.int32, device)
+    s_tf = _empty(total, t.int32, device)
+    row_nnz = _empty(n_docs + 1, t.int32, device)
+    _lib.check(L.sg_tfidf_count(_ptr(d_bytes), _ptr(d_off), n_docs, int(ngram), int(flags), _ptr(df), _ptr(s_clean),
+                                _ptr(s_sort), _ptr(s_key), _ptr(s_tf), _ptr(row_nnz), _stream()))
+    indptr = _empty(n_docs + 1, t.int64, device)
+    indices = _empty(total, t.int32, device)
+    val32 = _empty(total, t.float32, device)
+    val64 = _empty(total, t.float64, device) if np_dtype == np.float64 else None
+    tail = t.zeros(2, dtype=t.int64, device=device)         # [0] V (int32 view), [1] nnz
+    ws_bytes = int(L.sg_tfidf_finalize_workspace_bytes(n_docs, int(ngram)))
+    ws = _empty(ws_bytes, t.uint8, device)
+    dt = _lib.SG_DTYPE_F32 if np_dtype == np.float32 else _lib.SG_DTYPE_F64
+    _lib.check(L.sg_tfidf_finalize(_ptr(d_off), n_docs, int(ngram), dt, _ptr(df), _ptr(rank), _ptr(s_key), _ptr(s_tf),
+                                   _ptr(row_nnz), _ptr(indptr), _ptr(indices), _ptr(val64), _ptr(val32),
+                                   ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
+                                   ws_bytes, _stream()))
+    LAUNCH_COUNTS["tfidf"] += 5
+    n_master = int(n_master)
+    head = t.cat([tail, indptr[n_master:n_master + 1]]).cpu().numpy()     # one read-back: V, nnz, split point
+    V = int(head[0:1].view(np.int32)[0])
+    nnz = int(head[1])
+    split = int(head[2])
+    val = val64 if np_dtype == np.float64 else val32
+    vocab = DeviceVocabulary(df, rank, ngram, n_docs, V)
+    if stats is not None:
+        stats.update(n_docs=n_docs, total_bytes=total, nnz=nnz, vocab=V)
+    master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
+    if n_master == n_docs:
+        return master, None, vocab
+    dup = DeviceCSR((n_docs - n_master, V), indptr[n_master:], indices, val, val32, nnz - split, np_dtype, 1.0,
+                    base=split)
+    return master, dup, vocab
+
+
+def as_device_matches(m):
+    return m if isinstance(m, DeviceMatches) else matches_from_scipy(m)
+
+
+def apply_pending(m):
+    """Run the recorded _fix_diagonal / _symmetrize_matrix steps as one K4 launch (string_grouper.py:419-427:
+    the LIL round trip also re-orders every row by column, which K4 does even when only one step is set)."""
+    m = as_device_matches(m)
+    return symmetrize(m, fix_diagonal=m.pending_fix_diagonal, mirror=m.pending_mirror)

@@ -19,6 +19,8 @@ SG_DTYPE_F32 = 0
 SG_DTYPE_F64 = 1
 SG_FLAG_IGNORE_CASE = 1
 SG_FLAG_STRIP_DEFAULT = 2
+SG_SYMM_FIX_DIAGONAL = 1
+SG_SYMM_MIRROR = 2
 
 _i64 = ctypes.c_int64
 _i32 = ctypes.c_int
@@ -34,10 +36,10 @@ SIGNATURES = {
     "sg_abi_version": (_i32, []),
     "sg_device_info": (_i32, [_p, _p, _p]),
     "sg_tfidf_table_slots": (_i64, [_i32]),
-    "sg_tfidf_count": (_i32, [_p, _p, _i64, _i32, _u32, _p, _p, _p, _p, _p]),
+    "sg_tfidf_count": (_i32, [_p, _p, _i64, _i32, _u32, _p, _p, _p, _p, _p, _p, _p]),
     "sg_tfidf_finalize_workspace_bytes": (_sz, [_i64, _i32]),
-    "sg_tfidf_finalize": (_i32, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "sg_tfidf_vocab_keys": (_i32, [_p, _i32, _p, _p, _p]),
+    "sg_tfidf_finalize": (_i32, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_tfidf_vocab_keys": (_i32, [_p, _p, _i32, _p, _p]),
     "sg_num_tiles": (_i64, [_i64, _i32]),
     "sg_postings_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _sz, _p]),
@@ -47,7 +49,7 @@ SIGNATURES = {
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_symmetrize_workspace_bytes": (_sz, [_i64, _i64]),
-    "sg_symmetrize": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_symmetrize": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_rowwise_dot": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
 }
 

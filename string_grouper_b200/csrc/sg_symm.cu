@@ -18,20 +18,25 @@
 
 namespace sg {
 
-__global__ void symm_keys_kernel(int64_t n, int64_t nnz, const int32_t *__restrict__ row,
-                                 const int32_t *__restrict__ col, uint64_t *__restrict__ keys,
-                                 uint32_t *__restrict__ vals) {
+// layout of the key array: [0,nnz) stored entries, then (mirror ? [nnz,2nnz) transposes : nothing),
+// then (fix_diag ? n diagonal keys : nothing)
+__global__ void symm_keys_kernel(int64_t n, int64_t nnz, int mirror, int fix_diag,
+                                 const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) {
         const uint64_t r = (uint32_t)row[i], c = (uint32_t)col[i];
-        keys[2 * i] = (r << 32) | c;
-        keys[2 * i + 1] = (c << 32) | r;
-        vals[2 * i] = (uint32_t)i;
-        vals[2 * i + 1] = (uint32_t)i;
-    } else if (i < nnz + n) {
+        keys[i] = (r << 32) | c;
+        vals[i] = (uint32_t)i;
+        if (mirror) {
+            keys[nnz + i] = (c << 32) | r;
+            vals[nnz + i] = (uint32_t)i;
+        }
+    } else if (fix_diag && i < nnz + n) {
         const uint64_t r = (uint64_t)(i - nnz);
-        keys[nnz + i] = (r << 32) | r;
-        vals[nnz + i] = 0xffffffffu;
+        const int64_t o = (mirror ? 2 * nnz : nnz) + (i - nnz);
+        keys[o] = (r << 32) | r;
+        vals[o] = 0xffffffffu;
     }
 }
 
@@ -43,7 +48,7 @@ __global__ void symm_flag_kernel(int64_t m, const uint64_t *__restrict__ keys, i
 
 __global__ void symm_write_kernel(int64_t m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                   const int64_t *__restrict__ pos, const double *__restrict__ score,
-                                  int32_t *__restrict__ out_row, int32_t *__restrict__ out_col,
+                                  int fix_diag, int32_t *__restrict__ out_row, int32_t *__restrict__ out_col,
                                   double *__restrict__ out_score, int64_t *__restrict__ out_nnz) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -54,7 +59,7 @@ __global__ void symm_write_kernel(int64_t m, const uint64_t *__restrict__ keys, 
         const int64_t o = pos[i];
         out_row[o] = r;
         out_col[o] = c;
-        out_score[o] = (r == c) ? 1.0 : score[vals[i]];
+        out_score[o] = (fix_diag && r == c) ? 1.0 : score[vals[i]];
     }
     if (i == m - 1) *out_nnz = pos[i] + (first ? 1 : 0);
 }
@@ -81,12 +86,13 @@ size_t sg_symmetrize_workspace_bytes(int64_t nnz_in, int64_t n) {
            align_up(sort_bytes, 256) + align_up(scan_bytes, 256) + 4096;
 }
 
-int sg_symmetrize(int64_t n, int64_t nnz_in, const int32_t *in_row, const int32_t *in_col, const double *in_score,
-                  int32_t *out_row, int32_t *out_col, double *out_score, int64_t *out_nnz, void *ws,
-                  size_t ws_bytes, void *stream_) {
+int sg_symmetrize(int64_t n, int64_t nnz_in, int flags, const int32_t *in_row, const int32_t *in_col,
+                  const double *in_score, int32_t *out_row, int32_t *out_col, double *out_score, int64_t *out_nnz,
+                  void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n < 0 || nnz_in < 0) return fail(SG_ERR_INVALID, "negative size");
-    const int64_t m = 2 * nnz_in + n;
+    const int fix_diag = (flags & SG_SYMM_FIX_DIAGONAL) ? 1 : 0, mirror = (flags & SG_SYMM_MIRROR) ? 1 : 0;
+    const int64_t m = (mirror ? 2 : 1) * nnz_in + (fix_diag ? n : 0);
     if (m == 0) {
         SG_CUDA_TRY(cudaMemsetAsync(out_nnz, 0, sizeof(int64_t), st));
         return SG_OK;
@@ -107,7 +113,7 @@ int sg_symmetrize(int64_t n, int64_t nnz_in, const int32_t *in_row, const int32_
     if (!ar.ok()) return fail(SG_ERR_INVALID, "symmetrize workspace too small (%zu < %zu)", ws_bytes, ar.off);
 
     const unsigned g0 = (unsigned)((nnz_in + n + 255) / 256);
-    symm_keys_kernel<<<g0, 256, 0, st>>>(n, nnz_in, in_row, in_col, keys_in, vals_in);
+    symm_keys_kernel<<<g0, 256, 0, st>>>(n, nnz_in, mirror, fix_diag, in_row, in_col, keys_in, vals_in);
     SG_LAUNCH_CHECK();
     const int end_bit = 32 + bits_for64((uint64_t)(n > 0 ? n - 1 : 0));
     SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys, vals_in, vals, m, 0,
@@ -116,7 +122,8 @@ int sg_symmetrize(int64_t n, int64_t nnz_in, const int32_t *in_row, const int32_
     symm_flag_kernel<<<g1, 256, 0, st>>>(m, keys, flag);
     SG_LAUNCH_CHECK();
     SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flag, pos, m, st));
-    symm_write_kernel<<<g1, 256, 0, st>>>(m, keys, vals, pos, in_score, out_row, out_col, out_score, out_nnz);
+    symm_write_kernel<<<g1, 256, 0, st>>>(m, keys, vals, pos, in_score, fix_diag, out_row, out_col, out_score,
+                                          out_nnz);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }

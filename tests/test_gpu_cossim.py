@@ -38,7 +38,7 @@ def test_self_match_matches_oracle(n, top_n, thr, dtype):
     gr, gc, gs = got.host_triples()
     cut = row_cutoffs(ref.indptr, ref.data, top_n, n)
     st = compare_triples(csr_triples(ref), (gr, gc, gs), n, thr, cutoff_row=cut, label="self %d" % n)
-    assert st["common"] > n * 0.9          # at least the diagonal
+    assert st["common"] + st["boundary_ties"] >= n * 0.95   # at least the diagonal (ties may swap it)
     assert got.max_row == int(np.diff(ref.indptr).max())
     # entries of a row come out by descending score (sort=True, string_grouper.py:730)
     same_row = gr[1:] == gr[:-1]

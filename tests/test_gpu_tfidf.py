@@ -1,0 +1,102 @@
+"""-m gpu: K1 (device n-gram TF-IDF) against sklearn driven by the reference analyzer (the oracle) and against
+the reference's own matrix stored in tests/golden/synthetic.npz."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from synth_corpus import make_names
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "synthetic.npz"), allow_pickle=True)
+
+EDGE = ["", "ab", "abc", "A.B,C-D/E F\tG", "ÀbracâDABRÀ", "ﬁ½① İstanbul", "x" * 300 + " inc", "aaa aaa aaa aaaa"]
+
+
+def _device_matrices(master, dupes=None, **kw):
+    from string_grouper_b200 import StringGrouper
+    sg = StringGrouper(pd.Series(master), None if dupes is None else pd.Series(dupes), **kw)
+    m, d = sg._get_tf_idf_matrices()
+    return sg, m, d
+
+
+def _assert_same_csr(got, ref, rtol):
+    got, ref = got.to_scipy(), ref.tocsr()
+    assert got.shape == ref.shape
+    assert np.array_equal(got.indptr, ref.indptr)
+    assert np.array_equal(got.indices, ref.indices)
+    assert got.dtype == ref.dtype
+    np.testing.assert_allclose(got.data, ref.data, rtol=rtol, atol=0)
+
+
+def test_matrix_equals_reference_golden():
+    texts = make_names(500, seed=14) + EDGE
+    sg, m, _ = _device_matrices(texts)
+    got = m.to_scipy()
+    assert np.array_equal(got.indptr, GOLD["tfidf_indptr"]) and np.array_equal(got.indices, GOLD["tfidf_indices"])
+    np.testing.assert_allclose(got.data, GOLD["tfidf_data"], rtol=1e-14, atol=0)
+    assert sg._vocabulary.feature_names() == GOLD["tfidf_vocab"].tolist()
+    _, m32, _ = _device_matrices(texts, tfidf_matrix_dtype=np.float32)
+    assert m32.to_scipy().dtype == np.float32
+    np.testing.assert_allclose(m32.to_scipy().data, GOLD["tfidf32_data"], rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("kw", [{}, {"ngram_size": 2}, {"ngram_size": 4}, {"ngram_size": 1}, {"ignore_case": False},
+                                {"tfidf_matrix_dtype": np.float32}, {"regex": r"[aeiou\s]"}])
+def test_matrix_equals_sklearn_oracle(kw):
+    from oracle import pipeline as P
+    master = make_names(6000, seed=31) + EDGE + ["Q" * 1000, "lorem ipsum " * 60]
+    dupes = make_names(2500, seed=32) + ["zzzz", ""]
+    _, m, d = _device_matrices(master, dupes, **kw)
+    okw = dict(kw)
+    dtype = okw.pop("tfidf_matrix_dtype", np.float64)
+    rm, rd, _ = P.tf_idf_matrices(master, dupes, dtype=dtype, **okw)
+    rtol = 1e-14 if dtype == np.float64 else 2e-6
+    _assert_same_csr(m, rm, rtol)
+    _assert_same_csr(d, rd, rtol)
+
+
+def test_reference_fixture_build_matrix():
+    """test_build_matrix / test_build_matrix_master_and_duplicates (reference tests :519-544): exact values."""
+    _, m, d = _device_matrices(['foo', 'bar', 'baz'])
+    np.testing.assert_array_equal(m.toarray(), np.array([[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]]))
+    _, m, d = _device_matrices(['foo', 'bar', 'baz'], ['foo', 'bar', 'bop'])
+    np.testing.assert_array_equal(m.toarray(), np.array([[0., 0., 0., 1.], [1., 0., 0., 0.], [0., 1., 0., 0.]]))
+    np.testing.assert_array_equal(d.toarray(), np.array([[0., 0., 0., 1.], [1., 0., 0., 0.], [0., 0., 1., 0.]]))
+
+
+def test_full_pipeline_matches_oracle_fit():
+    from oracle import pipeline as P
+    from parity import compare_triples
+    from string_grouper_b200 import StringGrouper
+    names = make_names(20000, seed=41)
+    sg = StringGrouper(pd.Series(names)).fit()
+    got = sg._matches_list
+    ref, true_max = P.fit(names, n_threads=4, fast_symmetrize=True)
+    m, d, _ = P.tf_idf_matrices(names)
+    C = P.build_matches(m, d, None, 20, 0.8, n_threads=4)
+    from parity import row_cutoffs
+    cut = row_cutoffs(C.indptr, C.data, 20, len(names))
+    st = compare_triples((ref.master_side, ref.dupe_side, ref.similarity),
+                         (got.master_side, got.dupe_side, got.similarity), len(names), 0.8, tol=1e-9,
+                         cutoff_row=cut, cutoff_col=cut, label="fit 20k")
+    assert st["common"] >= 0.99 * st["pairs_ref"]
+    assert sg._true_max_n_matches == true_max
+    # storage order of the symmetrised list: row ascending, column ascending (ref test_get_matches_single)
+    key = got.master_side.to_numpy() * len(names) + got.dupe_side.to_numpy()
+    assert np.all(np.diff(key) > 0)
+
+
+def test_match_strings_two_series_frame_equals_oracle():
+    from oracle import pipeline as P
+    import string_grouper_b200 as api
+    master = pd.Series(make_names(5000, seed=51), name="company")
+    dupes = pd.Series(make_names(1500, seed=52) + make_names(5000, seed=51)[:500])
+    out = api.match_strings(master, dupes, min_similarity=0.75, max_n_matches=3)
+    ref, _ = P.fit(master.tolist(), dupes.tolist(), min_similarity=0.75, max_n_matches=3, n_threads=4)
+    assert list(out.columns) == ["left_index", "left_company", "similarity", "right_side", "right_index"]
+    a = set(zip(out.left_index.tolist(), out.right_index.tolist()))
+    b = set(zip(ref.master_side.tolist(), ref.dupe_side.tolist()))
+    assert len(a ^ b) <= 0.01 * len(b)         # top-3 ties between identical strings may differ
+    assert (out.left_company.to_numpy() == master.to_numpy()[out.left_index.to_numpy()]).all()
