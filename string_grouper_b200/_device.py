@@ -12,7 +12,7 @@ from . import _lib
 
 _TORCH = None
 
-# launch statistics of the last calls, read by bench.py ("gpu_launches")
+# hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0}
 
@@ -241,11 +241,17 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         cand_row = _empty(cap, t.int32, dev)
         cand_col = _empty(cap, t.int32, dev)
         counters.zero_()
+        if stats is not None and stats.get("time_kernels"):
+            ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(L.sg_cossim_candidates(
             _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
             _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, _ptr(cand_row), _ptr(cand_col), cap,
             ctypes.c_void_p(counters.data_ptr()), ctypes.c_void_p(counters.data_ptr() + 8), warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
+        if stats is not None and stats.get("time_kernels"):
+            ev1.record()
+            stats.setdefault("candidate_events", []).append((ev0, ev1))
         n_cand = int(counters[0].item())
         if n_cand <= cap:
             break
@@ -276,7 +282,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                 float(threshold), _ptr(out_indptr), _ptr(out_row), _ptr(out_col), _ptr(out_score),
                                 ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
                                 ws_bytes, _stream()))
-    LAUNCH_COUNTS["select"] += 6
+    LAUNCH_COUNTS["select"] += 5
     th = tail.cpu().numpy()
     nnz = int(th[0])
     max_row = int(th[1:2].view(np.int32)[0])
@@ -300,7 +306,7 @@ def symmetrize(M, fix_diagonal=True, mirror=True):
     ws = _empty(ws_bytes, t.uint8, dev)
     _lib.check(L.sg_symmetrize(n, M.nnz, flags, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), _ptr(out_row),
                                _ptr(out_col), _ptr(out_score), _ptr(out_nnz), _ptr(ws), ws_bytes, _stream()))
-    LAUNCH_COUNTS["symmetrize"] += 5
+    LAUNCH_COUNTS["symmetrize"] += 3
     nnz = int(out_nnz.item())
     return DeviceMatches(M.shape, out_row, out_col, out_score, nnz, M.max_row, out_dtype=M.out_dtype)
 
@@ -354,8 +360,27 @@ class DeviceVocabulary:
         return decode_vocab_keys(keys[:self.size].cpu().numpy().view(np.uint32), self.ngram)
 
 
+def upload_strings(data, offsets, device=None):
+    """H2D of the packed strings: (uint8 bytes, int64 offsets) -> device tensors."""
+    t = require_cuda()
+    device = device or t.device("cuda", t.cuda.current_device())
+    total = int(offsets[-1])
+    d_bytes = (t.from_numpy(np.ascontiguousarray(data)).to(device, non_blocking=True) if total
+               else _empty(1, t.uint8, device))
+    d_off = t.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
+    return d_bytes, d_off, total
+
+
 def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None):
-    """K1: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM.
+    """K1 from host buffers: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM."""
+    d_bytes, d_off, total = upload_strings(data, offsets, device)
+    if stats is not None:
+        stats["h2d_bytes"] = int(total + 8 * len(offsets))
+    return tfidf_resident(d_bytes, d_off, len(offsets) - 1, total, n_master, ngram, flags, dtype, stats=stats)
+
+
+def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype, stats=None):
+    """K1 on strings already resident in HBM.
 
     Device counterpart of _fit_vectorizer + transform (string_grouper.py:685-707): the vocabulary /
     df / idf are fitted on ALL rows, then rows [0, n_master) form the master matrix and the rest the
@@ -363,15 +388,11 @@ def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None)
     """
     t = require_cuda()
     L = _lib.load()
-    device = device or t.device("cuda", t.cuda.current_device())
-    n_docs = len(offsets) - 1
-    total = int(offsets[-1])
+    device = d_off.device
     slots = int(L.sg_tfidf_table_slots(int(ngram)))
     if slots < 0:
         raise NotImplementedError("ngram_size=%r: the device vectoriser supports 1 <= ngram_size <= 4" % (ngram,))
     np_dtype = np.float32 if np.dtype(dtype) == np.float32 else np.float64
-    d_bytes = t.from_numpy(np.ascontiguousarray(data)).to(device, non_blocking=True) if total else _empty(1, t.uint8, device)
-    d_off = t.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
     df = t.zeros(slots, dtype=t.int32, device=device)
     rank = _empty(slots, t.int32, device)
     s_clean = _empty(total, t.uint8, device)
@@ -393,7 +414,7 @@ def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None)
                                    _ptr(row_nnz), _ptr(indptr), _ptr(indices), _ptr(val64), _ptr(val32),
                                    ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
                                    ws_bytes, _stream()))
-    LAUNCH_COUNTS["tfidf"] += 5
+    LAUNCH_COUNTS["tfidf"] += 4
     n_master = int(n_master)
     head = t.cat([tail, indptr[n_master:n_master + 1]]).cpu().numpy()     # one read-back: V, nnz, split point
     V = int(head[0:1].view(np.int32)[0])
@@ -413,6 +434,17 @@ def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None)
 
 def as_device_matches(m):
     return m if isinstance(m, DeviceMatches) else matches_from_scipy(m)
+
+
+def gather_shards(m):
+    """Multi-GPU: all-gather the per-rank top-n lists (each rank computed its own block of left rows) so that
+    every rank holds the full result in row order; the `vstack` of string_grouper.py:750 over NVLink."""
+    from . import _dist
+    row, col, score, nnz, max_row = _dist.gather_matches(m.shape, m.d_row, m.d_col, m.d_score, m.nnz, m.max_row)
+    t = torch()
+    if nnz == 0:
+        row, col, score = _empty(1, t.int32, row.device), _empty(1, t.int32, row.device), _empty(1, t.float64, row.device)
+    return DeviceMatches(m.shape, row, col, score, nnz, max_row, out_dtype=m.out_dtype)
 
 
 def apply_pending(m):

@@ -242,8 +242,15 @@ __global__ void select_segments_kernel(int64_t n, const uint64_t *__restrict__ k
     seg[r] = lo;
 }
 
-// better(x, y): x ranks before y  (score desc, then position asc == column asc)
-__device__ __forceinline__ bool ranks_before(double sx, int64_t px, double sy, int64_t py) {
+// Which entries survive the top-n cut: larger score first; among EQUAL scores the larger column wins.
+// (sp_matmul_topn walks its touched-column list in reverse first-touch order and only replaces the heap
+// minimum on a strictly greater score, so among exact ties - identical strings - the highest column ids
+// are the ones it keeps)
+__device__ __forceinline__ bool kept_before(double sx, int64_t px, double sy, int64_t py) {
+    return sx > sy || (sx == sy && px > py);
+}
+// Order in which the survivors are written: score descending, column ascending among ties (sort=True).
+__device__ __forceinline__ bool written_before(double sx, int64_t px, double sy, int64_t py) {
     return sx > sy || (sx == sy && px < py);
 }
 
@@ -278,6 +285,7 @@ __global__ void select_write_kernel(int64_t n_rows, int64_t row_begin, const int
     const int lane = lane_id();
     const double NEG = -1.0e300;
     if (e - s <= 32) {
+        // one candidate per lane (segment is ordered by column): rank by all-to-all shuffles
         const int64_t p = s + lane;
         double sc = NEG;
         int32_t col = 0;
@@ -286,33 +294,69 @@ __global__ void select_write_kernel(int64_t n_rows, int64_t row_begin, const int
             if (v > thr) sc = v;
             col = (int32_t)(keys[p] & 0xffffffffu);
         }
-        int rank = 0;
+        int krank = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const double sj = __shfl_sync(FULL, sc, j);
-            rank += ranks_before(sj, j, sc, lane) ? 1 : 0;
+            krank += kept_before(sj, j, sc, lane) ? 1 : 0;
         }
-        if (sc > NEG && rank < top_n) {
-            out_row[ob + rank] = (int32_t)(r + row_begin);
-            out_col[ob + rank] = col;
-            out_score[ob + rank] = sc;
+        const bool kept = sc > NEG && krank < top_n;
+        const double ks = kept ? sc : NEG;
+        int wrank = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double sj = __shfl_sync(FULL, ks, j);
+            wrank += (sj > NEG && written_before(sj, j, ks, lane)) ? 1 : 0;
+        }
+        if (kept) {
+            out_row[ob + wrank] = (int32_t)(r + row_begin);
+            out_col[ob + wrank] = col;
+            out_score[ob + wrank] = sc;
         }
         return;
     }
-    // long rows (clusters of near-identical strings): rank by counting, O(m^2 / 32) per row
+    // long rows (clusters of near-identical strings), O(m^2 / 32) per row:
+    // pass 1 finds the last survivor (the cut), pass 2 ranks the survivors for writing.
+    const int64_t n_out = out_indptr[r + 1] - ob;
+    if (n_out == 0) return;
+    double cut_s = NEG;
+    int64_t cut_p = -1;
+    for (int64_t base = s; base < e; base += 32) {
+        const int64_t p = base + lane;
+        bool is_cut = false;
+        double sc = NEG;
+        if (p < e) {
+            sc = score[vals[p]];
+            if (sc > thr) {
+                int64_t k = 0;
+                for (int64_t q = s; q < e && k < n_out; ++q) {
+                    const double sq = score[vals[q]];
+                    k += (sq > thr && kept_before(sq, q, sc, p)) ? 1 : 0;
+                }
+                is_cut = (k == n_out - 1);
+            }
+        }
+        const unsigned hit = __ballot_sync(FULL, is_cut);
+        if (hit) {
+            const int src = __ffs(hit) - 1;
+            cut_s = __shfl_sync(FULL, sc, src);
+            cut_p = __shfl_sync(FULL, p, src);
+            break;
+        }
+    }
     for (int64_t p = s + lane; p < e; p += 32) {
         const double sc = score[vals[p]];
         if (!(sc > thr)) continue;
-        int64_t rank = 0;
-        for (int64_t q = s; q < e && rank < top_n; ++q) {
+        if (!(p == cut_p || kept_before(sc, p, cut_s, cut_p))) continue;
+        int64_t w = 0;
+        for (int64_t q = s; q < e; ++q) {
             const double sq = score[vals[q]];
-            rank += (sq > thr && ranks_before(sq, q, sc, p)) ? 1 : 0;
+            const bool q_kept = sq > thr && (q == cut_p || kept_before(sq, q, cut_s, cut_p));
+            w += (q_kept && written_before(sq, q, sc, p)) ? 1 : 0;
         }
-        if (rank < top_n) {
-            out_row[ob + rank] = (int32_t)(r + row_begin);
-            out_col[ob + rank] = (int32_t)(keys[p] & 0xffffffffu);
-            out_score[ob + rank] = sc;
-        }
+        out_row[ob + w] = (int32_t)(r + row_begin);
+        out_col[ob + w] = (int32_t)(keys[p] & 0xffffffffu);
+        out_score[ob + w] = sc;
     }
 }
 

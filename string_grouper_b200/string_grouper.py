@@ -26,7 +26,7 @@ from loguru import logger
 from scipy.sparse import csr_matrix
 from scipy.sparse.csgraph import connected_components
 
-from . import _device, _ingest
+from . import _device, _dist, _ingest
 
 DEFAULT_NGRAM_SIZE: int = 3
 DEFAULT_TFIDF_MATRIX_DTYPE: type = np.float64
@@ -282,7 +282,16 @@ class StringGrouper(object):
         """
         A = _device.as_device_csr(master_matrix)
         B = A if duplicate_matrix is master_matrix else _device.as_device_csr(duplicate_matrix)
-        out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity, stats=self._last_stats)
+        rank, world_size = _dist.world()
+        if world_size > 1:
+            # one process per GPU: this rank computes its block of left rows, the blocks are all-gathered
+            lo, hi = _dist.shard_range(A.shape[0], rank, world_size)
+            out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity, row_begin=lo,
+                                      row_end=hi, stats=self._last_stats)
+            out = _device.gather_shards(out)
+        else:
+            out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity,
+                                      stats=self._last_stats)
         if n_blocks is not None and A.dtype != np.float64:
             # ref:750 `vstack(Czip, dtype=np.float64)`: scipy's astype() de-duplicates when the dtype changes,
             # which re-orders every row by ascending column — float32 runs of the reference come out that way.

@@ -78,11 +78,27 @@ def as_device_csr(m):
     return m if isinstance(m, FakeCSR) else FakeCSR(m)
 
 
-def cossim_topn(A, B, top_n, threshold, **kw):
+def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, **kw):
     if A.shape[1] == 0:
         return FakeMatches(csr_matrix((A.shape[0], B.shape[0])), 0)
-    C = sp_matmul_topn(A.m, B.m.T, top_n=top_n, threshold=threshold, sort=True, n_threads=1)
-    return FakeMatches(C)
+    row_end = A.shape[0] if row_end is None else row_end
+    C = sp_matmul_topn(A.m[row_begin:row_end], B.m.T, top_n=top_n, threshold=threshold, sort=True, n_threads=1)
+    full = csr_matrix((C.data, C.indices, np.concatenate([np.zeros(row_begin, C.indptr.dtype), C.indptr,
+                                                          np.full(A.shape[0] - row_end, C.indptr[-1], C.indptr.dtype)])),
+                      shape=(A.shape[0], B.shape[0]))
+    return FakeMatches(full, max_row=int(np.diff(C.indptr).max()) if C.shape[0] else 0)
+
+
+def gather_shards(m):
+    import torch
+    from string_grouper_b200 import _dist
+    r, c, s = m.host_triples()
+    row, col, score, nnz, max_row = _dist.gather_matches(
+        m.shape, torch.from_numpy(r.astype(np.int32)), torch.from_numpy(c.astype(np.int32)),
+        torch.from_numpy(s.astype(np.float64)), len(r), m.max_row)
+    indptr = np.zeros(m.shape[0] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(row.numpy(), minlength=m.shape[0]), out=indptr[1:])
+    return FakeMatches(csr_matrix((score.numpy(), col.numpy(), indptr), shape=m.shape), max_row=max_row)
 
 
 def as_device_matches(m):
@@ -112,13 +128,14 @@ def rowwise_dot(A, B):
 @contextlib.contextmanager
 def oracle_device():
     names = ["tfidf", "as_device_csr", "cossim_topn", "as_device_matches", "apply_pending", "rowwise_dot",
-             "DeviceMatches", "symmetrize"]
+             "DeviceMatches", "symmetrize", "gather_shards"]
     saved = {n: getattr(_device, n) for n in names}
     try:
         _device.tfidf, _device.as_device_csr, _device.cossim_topn = tfidf, as_device_csr, cossim_topn
         _device.as_device_matches, _device.apply_pending, _device.rowwise_dot = as_device_matches, apply_pending, rowwise_dot
         _device.DeviceMatches = FakeMatches
         _device.symmetrize = symmetrize
+        _device.gather_shards = gather_shards
         yield
     finally:
         for n, v in saved.items():
