@@ -126,16 +126,18 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
  * candidate list.  `cand_count` [dev] (zeroed by the caller) ends up holding
  * the number of candidates FOUND, which may exceed `cand_cap` (then only the
  * first cand_cap were stored and the caller re-runs with a larger buffer).
- * `row_queue` [dev] (zeroed) is the dynamic work queue.
- * smem_bytes_hint: 0 = pick the largest configuration the device allows.
+ * `row_queue` [dev] (zeroed) is the dynamic work queue over (column-tile group, left row) items,
+ * groups outermost, `tiles_per_group` column tiles per group (sized by the caller so that one
+ * group's posting buckets stay L2-resident).
  */
 int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
                          int64_t n_right, int64_t n_cols, const int32_t *bucket_ptr /*[dev]*/,
                          const void *postings /*[dev]*/, int tile_w, float cand_threshold,
-                         int32_t *cand_row /*[dev] cap*/, int32_t *cand_col /*[dev] cap*/,
-                         int64_t cand_cap, unsigned long long *cand_count /*[dev] 1*/,
-                         int32_t *row_queue /*[dev] 1*/, int warps_per_cta, void *stream);
+                         int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
+                         int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
+                         unsigned long long *cand_count /*[dev] 1*/,
+                         unsigned long long *row_queue /*[dev] 1*/, int warps_per_cta, void *stream);
 
 /*
  * Exact re-scoring of the candidates: sorted-merge dot product of left row i

@@ -16,8 +16,9 @@ _TORCH = None
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0}
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "3072"))
-DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "16"))
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "1536"))
+DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
+GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 2.0e-4   # fp32 candidate scores are re-scored exactly; see DESIGN.md §K2
 
 
@@ -235,7 +236,9 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     scale = A.norm_bound * B.norm_bound
     thr_c = max(float(threshold) - CAND_MARGIN * max(scale, 1.0), 0.0)
 
-    counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] row_queue (int32 view)
+    # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
+    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
+    counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or (16 * n_rows + (1 << 20))
     for attempt in range(3):
         cand_row = _empty(cap, t.int32, dev)
@@ -246,7 +249,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             ev0.record()
         _lib.check(L.sg_cossim_candidates(
             _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
-            _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, _ptr(cand_row), _ptr(cand_col), cap,
+            _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, tiles_per_group, _ptr(cand_row), _ptr(cand_col), cap,
             ctypes.c_void_p(counters.data_ptr()), ctypes.c_void_p(counters.data_ptr() + 8), warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
         if stats is not None and stats.get("time_kernels"):
@@ -264,6 +267,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     if stats is not None:
         stats["n_candidates"] = n_cand
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
+        stats["tiles_per_group"] = tiles_per_group
 
     score = _empty(n_cand, t.float64, dev)
     _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),

@@ -43,7 +43,7 @@ SIGNATURES = {
     "sg_num_tiles": (_i64, [_i64, _i32]),
     "sg_postings_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _sz, _p]),
-    "sg_cossim_candidates": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _i32, _f32, _p, _p, _i64, _p,
+    "sg_cossim_candidates": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _i32, _f32, _i64, _p, _p, _i64, _p,
                                     _p, _i32, _p]),
     "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),

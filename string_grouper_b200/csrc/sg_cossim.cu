@@ -51,14 +51,14 @@ __global__ void postings_scatter_kernel(int64_t n_rows, const int64_t *__restric
 constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-privately
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32)
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                          const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
                          int64_t n_right, const int32_t *__restrict__ bptr,
-                         const uint2 *__restrict__ post, int W, int64_t T, float thr_c,
+                         const uint2 *__restrict__ post, int W, int64_t T, int64_t tiles_per_group, float thr_c,
                          int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
                          unsigned long long cap, unsigned long long *__restrict__ cand_count,
-                         int32_t *__restrict__ row_queue) {
+                         unsigned long long *__restrict__ row_queue) {
     extern __shared__ __align__(16) float smem_acc[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -67,16 +67,26 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
     for (int c = lane * 4; c < W; c += 128) *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
+    // Work item = (column-tile group, left row), groups outermost: at any moment every CTA of the grid streams
+    // posting buckets of the same few column tiles, so the live posting set stays L2-resident however
+    // large the right matrix is.
+    const int64_t n_rows = row_end - row_begin;
+    const int64_t n_groups = (T + tiles_per_group - 1) / tiles_per_group;
+    const unsigned long long n_items = (unsigned long long)n_rows * (unsigned long long)n_groups;
     for (;;) {
-        int64_t row = 0;
-        if (lane == 0) row = row_begin + atomicAdd(row_queue, 1);
-        row = __shfl_sync(FULL, row, 0);
-        if (row >= row_end) break;
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(row_queue, 1ull);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const int64_t group = (int64_t)(item / (unsigned long long)n_rows);
+        const int64_t row = row_begin + (int64_t)(item % (unsigned long long)n_rows);
         const int64_t p0 = a_indptr[row];
         const int nf = (int)(a_indptr[row + 1] - p0);
         if (nf == 0) continue;
+        const int64_t t_begin = group * tiles_per_group;
+        const int64_t t_end = t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T;
 
-        for (int64_t t = 0; t < T; ++t) {
+        for (int64_t t = t_begin; t < t_end; ++t) {
             const int c0 = (int)(t * W);
             for (int base = 0; base < nf; base += 32) {
                 const int k = base + lane;
@@ -430,19 +440,24 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 template <int NW>
 static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                              int64_t row_begin, int64_t row_end, int64_t n_right,
-                             const int32_t *bucket_ptr, const void *postings, int tile_w, float thr_c,
-                             int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
-                             unsigned long long *cand_count, int32_t *row_queue, int n_sm, cudaStream_t st) {
+                             const int32_t *bucket_ptr, const void *postings, int tile_w, int64_t tiles_per_group,
+                             float thr_c, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
+                             unsigned long long *cand_count, unsigned long long *row_queue, int n_sm,
+                             cudaStream_t st) {
     const size_t smem = (size_t)NW * tile_w * sizeof(float);
     SG_CUDA_TRY(cudaFuncSetAttribute(cossim_candidates_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t T = sg_num_tiles(n_right, tile_w);
     const int64_t n_rows = row_end - row_begin;
+    int per_sm = 1;
+    SG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cossim_candidates_kernel<NW>, NW * 32, smem));
+    if (per_sm < 1) per_sm = 1;
     int64_t ctas = (n_rows + NW - 1) / NW;
-    if (ctas > n_sm) ctas = n_sm;
+    if (ctas > (int64_t)n_sm * per_sm) ctas = (int64_t)n_sm * per_sm;   // persistent grid: resident CTAs x SMs
     if (ctas < 1) ctas = 1;
     cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
         a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr, (const uint2 *)postings, tile_w, T,
-        thr_c, cand_row, cand_col, (unsigned long long)cand_cap, cand_count, row_queue);
+        tiles_per_group < 1 ? 1 : tiles_per_group, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
+        cand_count, row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }
@@ -452,8 +467,8 @@ extern "C" {
 int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                          int64_t row_begin, int64_t row_end, int64_t n_right, int64_t n_cols,
                          const int32_t *bucket_ptr, const void *postings, int tile_w, float cand_threshold,
-                         int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
-                         unsigned long long *cand_count, int32_t *row_queue, int warps_per_cta,
+                         int64_t tiles_per_group, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
+                         unsigned long long *cand_count, unsigned long long *row_queue, int warps_per_cta,
                          void *stream_) {
     (void)n_cols;
     cudaStream_t st = (cudaStream_t)stream_;
@@ -470,8 +485,8 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, cons
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
         return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr,  \
-                                     postings, tile_w, cand_threshold, cand_row, cand_col, cand_cap,         \
-                                     cand_count, row_queue, n_sm, st);
+                                     postings, tile_w, tiles_per_group, cand_threshold, cand_row, cand_col,  \
+                                     cand_cap, cand_count, row_queue, n_sm, st);
     switch (warps_per_cta) {
         SG_CASE(4)
         SG_CASE(8)

@@ -12,7 +12,7 @@ names = make_names(n, 0)
 t = time.time(); m, d, _ = P.tf_idf_matrices(names, dtype=np.float64); print("oracle tfidf %.2fs nnz=%d V=%d" % (time.time() - t, m.nnz, m.shape[1]))
 macs = P.hot_path_macs(m, m); print("MACs %.4g  (%.3f per pair)" % (macs, macs / n / n))
 A = D.DeviceCSR.from_scipy(m)
-cfgs = [(3072, 16), (1536, 32), (6144, 8), (2048, 24), (1024, 32), (1536, 32)]
+cfgs = [(1536, 32), (3072, 16), (768, 32), (1024, 32), (2048, 24), (1536, 32)]
 if len(sys.argv) > 3:
     cfgs = [(int(sys.argv[2]), int(sys.argv[3]))]
 for tile_w, warps in cfgs:
