@@ -168,6 +168,43 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
                    void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * K2, formulation 2 (csrc/sg_order.cu, csrc/sg_cossim2.cu): same contract as sg_cossim_candidates —
+ * it feeds sg_rescore / sg_topn_select — but both operands are taken in heavy-feature signature order
+ * and a warp owns a tile of `rows_per_tile` left rows x `tile_w` columns, so one posting read serves
+ * every row of the tile and the lanes of a step hit distinct shared-memory banks.
+ * ------------------------------------------------------------------------- */
+size_t sg_order_workspace_bytes(int64_t n_rows, int64_t n_cols);
+/* hrank[n_cols] int8: rank among the n_heavy (<= 64) most frequent features of the matrix, else -1 */
+int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices, int n_heavy,
+                      int8_t *hrank /*[dev]*/, void *ws, size_t ws_bytes, void *stream);
+/* perm[i] = id of the i-th row of [row_begin,row_end) in signature order; rank = inverse (relative ids) */
+int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
+                 const int8_t *hrank, int32_t *perm /*[dev]*/, int32_t *rank /*[dev] or NULL*/, void *ws,
+                 size_t ws_bytes, void *stream);
+/* right matrix -> tile-major, column-sorted postings; bucket (t, f) at bucket_ptr[t*(n_cols+1)+f];
+ * `indptr` is the (possibly offset) row pointer of the n_rows right rows, indptr_base = indptr[0]. */
+size_t sg_postings2_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);
+int sg_postings2_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                       const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
+                       int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/, void *postings /*[dev] nnz*8 B*/, void *ws,
+                       size_t ws_bytes, void *stream);
+/* left rows perm[0..n_rows) -> per-tile lists sorted by feature.  row_pos[n_rows+1]; tl_ra[nnz] {row, w};
+ * seg_f / seg_start [nnz + n_tiles + 1] (tile t at row_pos[t*R] + t); tile_nseg[n_tiles]. */
+size_t sg_left_tiles_workspace_bytes(int64_t n_rows, int64_t nnz);
+int sg_left_tiles_build(int64_t n_rows, int64_t nnz, int rows_per_tile, const int64_t *indptr,
+                        const int32_t *indices, const float *val32, const int32_t *perm, int64_t *row_pos,
+                        void *tl_ra, int32_t *seg_f, int32_t *seg_start, int32_t *tile_nseg, void *ws,
+                        size_t ws_bytes, void *stream);
+size_t sg_cossim2_smem_bytes(int warps_per_cta, int rows_per_tile, int tile_w);
+int sg_cossim2_candidates(const int64_t *row_pos, const void *tl_ra, const int32_t *seg_f, const int32_t *seg_start,
+                          const int32_t *tile_nseg, int64_t n_left_rows, const int32_t *perm_a,
+                          const int32_t *bucket_ptr, const void *postings, int64_t n_cols, int tile_w,
+                          int64_t tiles_per_group, int64_t n_right, const int32_t *perm_b, float cand_threshold,
+                          int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
+                          unsigned long long *cand_count /*[dev] 1*/, unsigned long long *queue /*[dev] 1*/,
+                          int warps_per_cta, int rows_per_tile, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * K4 — self-match post-processing.
  * Replaces: _fix_diagonal + _symmetrize_matrix on LIL (sg.py:419-427,
  * :955-964): diagonal := 1 for every row, pattern := pattern U pattern^T,

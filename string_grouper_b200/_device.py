@@ -14,11 +14,15 @@ _TORCH = None
 
 # hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
-                 "rowdot": 0}
+                 "rowdot": 0, "order": 0, "tiles": 0}
 
 DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "1536"))
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
+K2_ALGO = int(os.environ.get("SG_B200_K2", "1"))            # 1 = row-wise (default), 2 = experimental tiled formulation
+V2_TILE_W = int(os.environ.get("SG_B200_V2_TILE_W", "320"))
+V2_WARPS = int(os.environ.get("SG_B200_V2_WARPS", "16"))
+V2_ROWS = int(os.environ.get("SG_B200_V2_ROWS", "8"))
 CAND_MARGIN = 2.0e-4   # fp32 candidate scores are re-scored exactly; see DESIGN.md §K2
 
 
@@ -67,10 +71,13 @@ class DeviceCSR:
         self.d_indptr, self.d_indices, self.d_val, self.d_val32 = indptr, indices, val, val32
         self.base = int(base)
         self.nnz = int(nnz)
+        self.nnz_parent = int(nnz)     # stored values of the whole array a row-range view points into
         self.dtype = np.dtype(dtype)
         self.norm_bound = float(norm_bound)
         self._host = None
         self._postings = {}
+        self._order = None          # (hrank, perm, rank) in heavy-feature signature order
+        self._postings2 = {}
 
     @property
     def device(self):
@@ -151,6 +158,82 @@ def build_postings(B, tile_w):
     return bucket_ptr, post, T
 
 
+def heavy_features(B):
+    """int8 rank of every feature among the 64 most frequent ones of B (-1 otherwise)."""
+    t = require_cuda()
+    L = _lib.load()
+    n_rows, n_cols = B.shape
+    hrank = _empty(n_cols, t.int8, B.device)
+    ws_bytes = int(L.sg_order_workspace_bytes(n_rows, n_cols))
+    ws = _empty(ws_bytes, t.uint8, B.device)
+    _lib.check(L.sg_heavy_features(n_rows, n_cols, _ptr(B.d_indptr), _ptr(B.d_indices), 64, _ptr(hrank), _ptr(ws),
+                                   ws_bytes, _stream()))
+    LAUNCH_COUNTS["order"] += 4
+    return hrank
+
+
+def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True):
+    """(perm, rank) of rows [row_begin,row_end) of M sorted by heavy-feature signature."""
+    t = require_cuda()
+    L = _lib.load()
+    row_end = M.shape[0] if row_end is None else row_end
+    n = max(row_end - row_begin, 0)
+    perm = _empty(n, t.int32, M.device)
+    rank = _empty(n, t.int32, M.device) if want_rank else None
+    ws_bytes = int(L.sg_order_workspace_bytes(max(n, 1), M.shape[1]))
+    ws = _empty(ws_bytes, t.uint8, M.device)
+    _lib.check(L.sg_row_order(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(hrank), _ptr(perm),
+                              _ptr(rank), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["order"] += 2
+    return perm, rank
+
+
+def right_side_v2(B, tile_w):
+    """Signature order + tile-major column-sorted postings of the right matrix, cached on B."""
+    t = require_cuda()
+    L = _lib.load()
+    if B._order is None:
+        hrank = heavy_features(B)
+        perm, rank = row_order(B, hrank)
+        B._order = (hrank, perm, rank)
+    hrank, perm, rank = B._order
+    if tile_w not in B._postings2:
+        n_rows, n_cols = B.shape
+        T = int(L.sg_num_tiles(n_rows, tile_w))
+        nb = T * (n_cols + 1) + 1
+        if nb >= 2**31 - 1:
+            raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
+        bucket_ptr = _empty(nb, t.int32, B.device)
+        post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
+        ws_bytes = int(L.sg_postings2_workspace_bytes(B.nnz, n_cols, T))
+        ws = _empty(ws_bytes, t.uint8, B.device)
+        _lib.check(L.sg_postings2_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
+                                        _ptr(rank), tile_w, B.base, _ptr(bucket_ptr), _ptr(post), _ptr(ws), ws_bytes,
+                                        _stream()))
+        LAUNCH_COUNTS["postings"] += 2
+        B._postings2[tile_w] = (bucket_ptr, post, T)
+    return (hrank, perm, rank) + B._postings2[tile_w]
+
+
+def left_tiles_v2(A, perm, n_rows, rows_per_tile):
+    t = require_cuda()
+    L = _lib.load()
+    n_tiles = (n_rows + rows_per_tile - 1) // rows_per_tile
+    nnz_cap = A.nnz if (n_rows == A.shape[0]) else A.nnz_parent
+    row_pos = _empty(n_rows + 1, t.int64, A.device)
+    tl_ra = _empty(2 * max(nnz_cap, 1), t.int32, A.device)
+    seg_f = _empty(nnz_cap + n_tiles + 1, t.int32, A.device)
+    seg_start = _empty(nnz_cap + n_tiles + 1, t.int32, A.device)
+    tile_nseg = _empty(n_tiles, t.int32, A.device)
+    ws_bytes = int(L.sg_left_tiles_workspace_bytes(n_rows, nnz_cap))
+    ws = _empty(ws_bytes, t.uint8, A.device)
+    _lib.check(L.sg_left_tiles_build(n_rows, nnz_cap, rows_per_tile, _ptr(A.d_indptr), _ptr(A.d_indices),
+                                     _ptr(A.d_val32), _ptr(perm), _ptr(row_pos), _ptr(tl_ra), _ptr(seg_f),
+                                     _ptr(seg_start), _ptr(tile_nseg), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["tiles"] += 2
+    return row_pos, tl_ra, seg_f, seg_start, tile_nseg
+
+
 class DeviceMatches:
     """Result of the top-n product in HBM: COO triples ordered by (row asc, score desc)
     or, after symmetrize(), by (row asc, col asc).  Lazily materialises the scipy CSR that
@@ -207,7 +290,8 @@ def pick_tile(n_right, tile_w=None, warps=None):
     return min(tile_w, need), warps
 
 
-def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None):
+def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None, algo=None,
+                rows_per_tile=None):
     """C[i,:] = top_n{ j : A_i . B_j > threshold } for rows [row_begin,row_end) of A.
 
     Device counterpart of the whole block loop of StringGrouper._build_matches
@@ -231,15 +315,33 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         z32 = _empty(1, t.int32, dev)
         return DeviceMatches(shape, z32, z32, _empty(1, t.float64, dev), 0, 0)
 
-    tile_w, warps = pick_tile(n_right, tile_w, warps)
-    bucket_ptr, post, T = B.postings(tile_w)
+    algo = int(algo or K2_ALGO)
     scale = A.norm_bound * B.norm_bound
     thr_c = max(float(threshold) - CAND_MARGIN * max(scale, 1.0), 0.0)
-
-    # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
-    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
-    cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or (16 * n_rows + (1 << 20))
+    # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
+    # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
+    cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
+    if algo == 2:
+        rows_per_tile = int(rows_per_tile or V2_ROWS)
+        warps = int(warps or V2_WARPS)
+        tile_w = min(int(tile_w or V2_TILE_W), ((n_right + 31) // 32) * 32)
+        smem_optin = ctypes.c_int(0)
+        _lib.check(L.sg_device_info(None, ctypes.byref(smem_optin), None))
+        while warps > 8 and int(L.sg_cossim2_smem_bytes(warps, rows_per_tile, tile_w)) > smem_optin.value:
+            warps -= 8
+        hrank, perm_b, rank_b, bucket_ptr, post, T = right_side_v2(B, tile_w)
+        if A is B and row_begin == 0 and row_end == n_left:
+            perm_a = perm_b
+        else:
+            perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
+        row_pos, tl_ra, seg_f, seg_start, tile_nseg = left_tiles_v2(A, perm_a, n_rows, rows_per_tile)
+        tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
+    else:
+        tile_w, warps = pick_tile(n_right, tile_w, warps)
+        bucket_ptr, post, T = B.postings(tile_w)
+        # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
+        tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
     for attempt in range(3):
         cand_row = _empty(cap, t.int32, dev)
         cand_col = _empty(cap, t.int32, dev)
@@ -247,10 +349,18 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         if stats is not None and stats.get("time_kernels"):
             ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             ev0.record()
-        _lib.check(L.sg_cossim_candidates(
-            _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
-            _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, tiles_per_group, _ptr(cand_row), _ptr(cand_col), cap,
-            ctypes.c_void_p(counters.data_ptr()), ctypes.c_void_p(counters.data_ptr() + 8), warps, _stream()))
+        c_count = ctypes.c_void_p(counters.data_ptr())
+        c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
+        if algo == 2:
+            _lib.check(L.sg_cossim2_candidates(
+                _ptr(row_pos), _ptr(tl_ra), _ptr(seg_f), _ptr(seg_start), _ptr(tile_nseg), n_rows, _ptr(perm_a),
+                _ptr(bucket_ptr), _ptr(post), A.shape[1], tile_w, tiles_per_group, n_right, _ptr(perm_b), thr_c,
+                _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, rows_per_tile, _stream()))
+        else:
+            _lib.check(L.sg_cossim_candidates(
+                _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
+                _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, tiles_per_group, _ptr(cand_row), _ptr(cand_col), cap,
+                c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
         if stats is not None and stats.get("time_kernels"):
             ev1.record()
@@ -267,7 +377,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     if stats is not None:
         stats["n_candidates"] = n_cand
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
-        stats["tiles_per_group"] = tiles_per_group
+        stats["tiles_per_group"], stats["algo"] = tiles_per_group, algo
 
     score = _empty(n_cand, t.float64, dev)
     _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
@@ -286,7 +396,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                 float(threshold), _ptr(out_indptr), _ptr(out_row), _ptr(out_col), _ptr(out_score),
                                 ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
                                 ws_bytes, _stream()))
-    LAUNCH_COUNTS["select"] += 5
+    LAUNCH_COUNTS["select"] += 7
     th = tail.cpu().numpy()
     nnz = int(th[0])
     max_row = int(th[1:2].view(np.int32)[0])
@@ -429,10 +539,12 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
     if stats is not None:
         stats.update(n_docs=n_docs, total_bytes=total, nnz=nnz, vocab=V)
     master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
+    master.nnz_parent = nnz
     if n_master == n_docs:
         return master, None, vocab
     dup = DeviceCSR((n_docs - n_master, V), indptr[n_master:], indices, val, val32, nnz - split, np_dtype, 1.0,
                     base=split)
+    dup.nnz_parent = nnz
     return master, dup, vocab
 
 

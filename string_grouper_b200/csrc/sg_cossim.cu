@@ -231,143 +231,88 @@ __global__ void rowwise_dot_kernel(int64_t n, const int64_t *__restrict__ a_indp
 // ---------------------------------------------------------------------------
 // top-n selection
 // ---------------------------------------------------------------------------
-__global__ void select_keys_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
-                                   int64_t row_begin, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+// Candidates are ordered by (row asc, score desc, column desc) with three stable LSD radix-sort passes
+// (column, score, row); candidates at or below the threshold are parked behind the last row.  The first
+// min(top_n, count) entries of a row segment are then exactly the survivors: larger score first and, among
+// EQUAL scores, the larger column (sp_matmul_topn walks its touched-column list in reverse first-touch order
+// and only replaces the heap minimum on a strictly greater score, so among exact ties - identical strings -
+// it keeps the highest column ids).  They are written score-descending with ties in
+// ascending column order (sort=True, string_grouper.py:730/:741).
+__global__ void select_init_kernel(int64_t n, const int32_t *__restrict__ cc, uint32_t *__restrict__ key_col,
+                                   uint32_t *__restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = ((uint64_t)(uint32_t)(cr[i] - (int32_t)row_begin) << 32) | (uint32_t)cc[i];
-    vals[i] = (uint32_t)i;
+    key_col[i] = ~(uint32_t)cc[i];          // descending column
+    idx[i] = (uint32_t)i;
 }
 
-__global__ void select_segments_kernel(int64_t n, const uint64_t *__restrict__ keys, int64_t n_rows,
+__global__ void select_score_keys_kernel(int64_t n, const uint32_t *__restrict__ idx, const double *__restrict__ score,
+                                         uint64_t *__restrict__ key_score) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t b = (uint64_t)__double_as_longlong(score[idx[i]]);
+    b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // order-preserving map of IEEE doubles to unsigned
+    key_score[i] = ~b;                                  // descending score
+}
+
+__global__ void select_row_keys_kernel(int64_t n, const uint32_t *__restrict__ idx, const int32_t *__restrict__ cr,
+                                       const double *__restrict__ score, double thr, int64_t row_begin,
+                                       int64_t n_rows, uint32_t *__restrict__ key_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = idx[i];
+    key_row[i] = score[c] > thr ? (uint32_t)(cr[c] - (int32_t)row_begin) : (uint32_t)n_rows;
+}
+
+__global__ void select_segments_kernel(int64_t n, const uint32_t *__restrict__ key_row, int64_t n_rows,
                                        int64_t *__restrict__ seg) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rows) return;
-    const uint64_t want = (uint64_t)r << 32;
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+        if ((int64_t)key_row[mid] < r) lo = mid + 1; else hi = mid;
     }
     seg[r] = lo;
 }
 
-// Which entries survive the top-n cut: larger score first; among EQUAL scores the larger column wins.
-// (sp_matmul_topn walks its touched-column list in reverse first-touch order and only replaces the heap
-// minimum on a strictly greater score, so among exact ties - identical strings - the highest column ids
-// are the ones it keeps)
-__device__ __forceinline__ bool kept_before(double sx, int64_t px, double sy, int64_t py) {
-    return sx > sy || (sx == sy && px > py);
-}
-// Order in which the survivors are written: score descending, column ascending among ties (sort=True).
-__device__ __forceinline__ bool written_before(double sx, int64_t px, double sy, int64_t py) {
-    return sx > sy || (sx == sy && px < py);
-}
-
-__global__ void select_count_kernel(int64_t n_rows, const int64_t *__restrict__ seg,
-                                    const uint32_t *__restrict__ vals, const double *__restrict__ score,
-                                    double thr, int top_n, int64_t *__restrict__ out_cnt,
-                                    int32_t *__restrict__ out_max) {
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void select_count_kernel(int64_t n_rows, const int64_t *__restrict__ seg, int top_n,
+                                    int64_t *__restrict__ out_cnt, int32_t *__restrict__ out_max) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int64_t s = seg[r], e = seg[r + 1];
-    int c = 0;
-    for (int64_t p = s + lane_id(); p < e; p += 32) c += score[vals[p]] > thr ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-    if (lane_id() == 0) {
-        const int k = c < top_n ? c : top_n;
-        out_cnt[r] = k;
-        if (k > 0) atomicMax(out_max, k);
-    }
+    const int64_t c = seg[r + 1] - seg[r];
+    const int k = (int)(c < top_n ? c : top_n);
+    out_cnt[r] = k;
+    if (k > 0) atomicMax(out_max, k);
 }
 
+// one thread per output entry; position inside the row = k, mirrored inside its run of equal scores
 __global__ void select_write_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restrict__ seg,
-                                    const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                    const double *__restrict__ score, double thr, int top_n,
-                                    const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_row,
-                                    int32_t *__restrict__ out_col, double *__restrict__ out_score) {
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= n_rows) return;
-    const int64_t s = seg[r], e = seg[r + 1];
-    if (s == e) return;
-    const int64_t ob = out_indptr[r];
-    const int lane = lane_id();
-    const double NEG = -1.0e300;
-    if (e - s <= 32) {
-        // one candidate per lane (segment is ordered by column): rank by all-to-all shuffles
-        const int64_t p = s + lane;
-        double sc = NEG;
-        int32_t col = 0;
-        if (p < e) {
-            const double v = score[vals[p]];
-            if (v > thr) sc = v;
-            col = (int32_t)(keys[p] & 0xffffffffu);
-        }
-        int krank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const double sj = __shfl_sync(FULL, sc, j);
-            krank += kept_before(sj, j, sc, lane) ? 1 : 0;
-        }
-        const bool kept = sc > NEG && krank < top_n;
-        const double ks = kept ? sc : NEG;
-        int wrank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const double sj = __shfl_sync(FULL, ks, j);
-            wrank += (sj > NEG && written_before(sj, j, ks, lane)) ? 1 : 0;
-        }
-        if (kept) {
-            out_row[ob + wrank] = (int32_t)(r + row_begin);
-            out_col[ob + wrank] = col;
-            out_score[ob + wrank] = sc;
-        }
-        return;
+                                    const uint32_t *__restrict__ idx, const int32_t *__restrict__ cc,
+                                    const double *__restrict__ score, const int64_t *__restrict__ out_indptr,
+                                    int32_t *__restrict__ out_row, int32_t *__restrict__ out_col,
+                                    double *__restrict__ out_score) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= out_indptr[n_rows]) return;
+    // row of this output slot: largest r with out_indptr[r] <= o
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (out_indptr[mid] <= o) lo = mid; else hi = mid - 1;
     }
-    // long rows (clusters of near-identical strings), O(m^2 / 32) per row:
-    // pass 1 finds the last survivor (the cut), pass 2 ranks the survivors for writing.
-    const int64_t n_out = out_indptr[r + 1] - ob;
-    if (n_out == 0) return;
-    double cut_s = NEG;
-    int64_t cut_p = -1;
-    for (int64_t base = s; base < e; base += 32) {
-        const int64_t p = base + lane;
-        bool is_cut = false;
-        double sc = NEG;
-        if (p < e) {
-            sc = score[vals[p]];
-            if (sc > thr) {
-                int64_t k = 0;
-                for (int64_t q = s; q < e && k < n_out; ++q) {
-                    const double sq = score[vals[q]];
-                    k += (sq > thr && kept_before(sq, q, sc, p)) ? 1 : 0;
-                }
-                is_cut = (k == n_out - 1);
-            }
-        }
-        const unsigned hit = __ballot_sync(FULL, is_cut);
-        if (hit) {
-            const int src = __ffs(hit) - 1;
-            cut_s = __shfl_sync(FULL, sc, src);
-            cut_p = __shfl_sync(FULL, p, src);
-            break;
-        }
-    }
-    for (int64_t p = s + lane; p < e; p += 32) {
-        const double sc = score[vals[p]];
-        if (!(sc > thr)) continue;
-        if (!(p == cut_p || kept_before(sc, p, cut_s, cut_p))) continue;
-        int64_t w = 0;
-        for (int64_t q = s; q < e; ++q) {
-            const double sq = score[vals[q]];
-            const bool q_kept = sq > thr && (q == cut_p || kept_before(sq, q, cut_s, cut_p));
-            w += (q_kept && written_before(sq, q, sc, p)) ? 1 : 0;
-        }
-        out_row[ob + w] = (int32_t)(r + row_begin);
-        out_col[ob + w] = (int32_t)(keys[p] & 0xffffffffu);
-        out_score[ob + w] = sc;
-    }
+    const int64_t r = lo;
+    const int64_t k = o - out_indptr[r];
+    const int64_t n_out = out_indptr[r + 1] - out_indptr[r];
+    const int64_t base = seg[r];
+    const uint32_t c = idx[base + k];
+    const double sc = score[c];
+    int64_t a = k, b = k + 1;                       // run [a, b) of equal scores among the survivors
+    while (a > 0 && score[idx[base + a - 1]] == sc) --a;
+    while (b < n_out && score[idx[base + b]] == sc) ++b;
+    const int64_t w = out_indptr[r] + a + (b - 1 - k);
+    out_row[w] = (int32_t)(r + row_begin);
+    out_col[w] = cc[c];
+    out_score[w] = sc;
 }
 
 __global__ void select_finish_kernel(int64_t n_rows, const int64_t *__restrict__ out_indptr,
@@ -538,12 +483,15 @@ int sg_rowwise_dot(int64_t n_rows, const int64_t *a_indptr, const int32_t *a_ind
 }
 
 size_t sg_topn_select_workspace_bytes(int64_t n_cand, int64_t n_rows) {
-    size_t sort_bytes = 0, scan_bytes = 0;
+    size_t s32 = 0, s64 = 0, scan_bytes = 0;
     const int64_t n = n_cand < 1 ? 1 : n_cand;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
-                                    (uint32_t *)nullptr, (uint32_t *)nullptr, n);
+    cub::DeviceRadixSort::SortPairs(nullptr, s32, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n);
+    cub::DeviceRadixSort::SortPairs(nullptr, s64, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int64_t *)nullptr, (int64_t *)nullptr, n_rows + 1);
-    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) +
+    const size_t sort_bytes = s32 > s64 ? s32 : s64;
+    return 2 * align_up((size_t)n * 8, 256) + 4 * align_up((size_t)n * 4, 256) +
            2 * align_up((size_t)(n_rows + 2) * 8, 256) + align_up(sort_bytes, 256) + align_up(scan_bytes, 256) + 4096;
 }
 
@@ -553,6 +501,7 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
                    int32_t *out_max_row, void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_rows < 0 || n_cand < 0) return fail(SG_ERR_INVALID, "negative size");
+    if (n_cand >= (int64_t)0xfffffff0u) return fail(SG_ERR_OVERFLOW, "too many candidates: %lld", (long long)n_cand);
     SG_CUDA_TRY(cudaMemsetAsync(out_max_row, 0, sizeof(int32_t), st));
     if (n_cand == 0 || top_n <= 0) {
         SG_CUDA_TRY(cudaMemsetAsync(out_indptr, 0, (size_t)(n_rows + 1) * sizeof(int64_t), st));
@@ -560,39 +509,53 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
         return SG_OK;
     }
     Arena ar(ws, ws_bytes);
-    uint64_t *keys_in = ar.take<uint64_t>((size_t)n_cand);
-    uint64_t *keys = ar.take<uint64_t>((size_t)n_cand);
-    uint32_t *vals_in = ar.take<uint32_t>((size_t)n_cand);
-    uint32_t *vals = ar.take<uint32_t>((size_t)n_cand);
+    uint64_t *k64_in = ar.take<uint64_t>((size_t)n_cand);
+    uint64_t *k64_out = ar.take<uint64_t>((size_t)n_cand);
+    uint32_t *k32_in = ar.take<uint32_t>((size_t)n_cand);
+    uint32_t *k32_out = ar.take<uint32_t>((size_t)n_cand);
+    uint32_t *idx_a = ar.take<uint32_t>((size_t)n_cand);
+    uint32_t *idx_b = ar.take<uint32_t>((size_t)n_cand);
     int64_t *seg = ar.take<int64_t>((size_t)n_rows + 2);
     int64_t *cnt = ar.take<int64_t>((size_t)n_rows + 2);
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, keys, vals_in, vals, n_cand);
+    size_t s32 = 0, s64 = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, s32, k32_in, k32_out, idx_a, idx_b, n_cand);
+    cub::DeviceRadixSort::SortPairs(nullptr, s64, k64_in, k64_out, idx_a, idx_b, n_cand);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, out_indptr, n_rows + 1);
+    size_t sort_bytes = s32 > s64 ? s32 : s64;
     char *sort_tmp = ar.take<char>(sort_bytes);
     char *scan_tmp = ar.take<char>(scan_bytes);
     if (!ar.ok()) return fail(SG_ERR_INVALID, "select workspace too small (%zu < %zu)", ws_bytes, ar.off);
 
     const unsigned g1 = (unsigned)((n_cand + 255) / 256);
-    select_keys_kernel<<<g1, 256, 0, st>>>(n_cand, cand_row, cand_col, row_begin, keys_in, vals_in);
+    // pass 1: column descending
+    select_init_kernel<<<g1, 256, 0, st>>>(n_cand, cand_col, k32_in, idx_a);
     SG_LAUNCH_CHECK();
-    const int end_bit = 32 + bits_for((uint64_t)(n_rows > 0 ? n_rows - 1 : 0));
-    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys, vals_in, vals, n_cand, 0,
-                                                end_bit > 64 ? 64 : end_bit, st));
+    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k32_in, k32_out, idx_a, idx_b, n_cand, 0, 32, st));
+    // pass 2: score descending (stable)
+    select_score_keys_kernel<<<g1, 256, 0, st>>>(n_cand, idx_b, score, k64_in);
+    SG_LAUNCH_CHECK();
+    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k64_in, k64_out, idx_b, idx_a, n_cand, 0, 64, st));
+    // pass 3: row ascending (stable); candidates not above the threshold go behind the last row
+    select_row_keys_kernel<<<g1, 256, 0, st>>>(n_cand, idx_a, cand_row, score, threshold, row_begin, n_rows, k32_in);
+    SG_LAUNCH_CHECK();
+    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k32_in, k32_out, idx_a, idx_b, n_cand, 0,
+                                                bits_for((uint64_t)n_rows), st));
     const unsigned g2 = (unsigned)((n_rows + 1 + 255) / 256);
-    select_segments_kernel<<<g2, 256, 0, st>>>(n_cand, keys, n_rows, seg);
+    select_segments_kernel<<<g2, 256, 0, st>>>(n_cand, k32_out, n_rows, seg);
     SG_LAUNCH_CHECK();
     SG_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(n_rows + 2) * sizeof(int64_t), st));
-    const int wpb = 8;
-    const unsigned g3 = (unsigned)((n_rows + wpb - 1) / wpb);
     if (n_rows > 0) {
-        select_count_kernel<<<g3, wpb * 32, 0, st>>>(n_rows, seg, vals, score, threshold, top_n, cnt, out_max_row);
+        select_count_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(n_rows, seg, top_n, cnt, out_max_row);
         SG_LAUNCH_CHECK();
     }
     SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cnt, out_indptr, n_rows + 1, st));
     if (n_rows > 0) {
-        select_write_kernel<<<g3, wpb * 32, 0, st>>>(n_rows, row_begin, seg, keys, vals, score, threshold, top_n,
-                                                     out_indptr, out_row, out_col, out_score);
+        // at most min(n_cand, n_rows * top_n) outputs; one thread each (threads beyond the total exit)
+        int64_t max_out = n_rows * (int64_t)top_n;
+        if (max_out > n_cand) max_out = n_cand;
+        select_write_kernel<<<(unsigned)((max_out + 255) / 256), 256, 0, st>>>(n_rows, row_begin, seg, idx_b, cand_col,
+                                                                              score, out_indptr, out_row, out_col,
+                                                                              out_score);
         SG_LAUNCH_CHECK();
     }
     select_finish_kernel<<<1, 32, 0, st>>>(n_rows, out_indptr, out_nnz);

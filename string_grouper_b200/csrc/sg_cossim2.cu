@@ -21,7 +21,12 @@
 namespace sg {
 
 constexpr int K2_LCAP = 192;   // tile-list entries kept in shared memory (longer lists are read from HBM/L2)
+constexpr int K2_LSEG = K2_LCAP + 4;   // segment slots (incl. sentinel), keeps the per-warp block 16-byte aligned
 constexpr int K2_SHORT = 4;    // buckets up to this length are walked lane-privately
+
+__host__ __device__ constexpr size_t k2_per_warp_bytes(int R, int Wc) {
+    return (size_t)R * Wc * 4 + (size_t)K2_LCAP * 8 + (size_t)K2_LSEG * 8;
+}
 
 // ---------------------------------------------------------------------------
 // postings, tile-major, column-sorted
@@ -174,12 +179,12 @@ cossim2_candidates_kernel(const int64_t *__restrict__ tile_ptr, const uint2 *__r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)R * Wc * 4 + (size_t)K2_LCAP * 8 + (size_t)(K2_LCAP + 1) * 8;
+    const size_t per_warp = k2_per_warp_bytes(R, Wc);
     unsigned char *mine = smem_raw + (size_t)warp * per_warp;
     float *acc = reinterpret_cast<float *>(mine);
     uint2 *s_ra = reinterpret_cast<uint2 *>(mine + (size_t)R * Wc * 4);
     int32_t *s_segf = reinterpret_cast<int32_t *>(s_ra + K2_LCAP);
-    int32_t *s_segs = s_segf + (K2_LCAP + 1);
+    int32_t *s_segs = s_segf + K2_LSEG;
     const int tile_elems = R * Wc;
 
     for (int c = lane * 4; c < tile_elems; c += 128) *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -429,6 +434,66 @@ int sg_left_tiles_build(int64_t n_rows, int64_t nnz, int R, const int64_t *indpt
         tile_nseg);
     SG_LAUNCH_CHECK();
     return SG_OK;
+}
+
+}  // extern "C"
+
+template <int NW, int R>
+static int launch_cossim2(const int64_t *row_pos, const void *tl_ra, const int32_t *seg_f, const int32_t *seg_start,
+                          const int32_t *tile_nseg, int64_t n_left_rows, const int32_t *perm_a,
+                          const int32_t *bucket_ptr, const void *postings, int64_t n_cols, int tile_w,
+                          int64_t tiles_per_group, int64_t n_right, const int32_t *perm_b, float thr_c,
+                          int32_t *cand_row, int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
+                          unsigned long long *queue, int n_sm, cudaStream_t st) {
+    const size_t smem = k2_per_warp_bytes(R, tile_w) * NW;
+    SG_CUDA_TRY(cudaFuncSetAttribute(cossim2_candidates_kernel<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    int per_sm = 1;
+    SG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cossim2_candidates_kernel<NW, R>, NW * 32, smem));
+    if (per_sm < 1) return fail(SG_ERR_INVALID, "cossim2: %zu bytes of shared memory per CTA do not fit", smem);
+    const int64_t T = sg_num_tiles(n_right, tile_w);
+    const int64_t n_tiles_left = (n_left_rows + R - 1) / R;
+    int64_t ctas = (n_tiles_left + NW - 1) / NW;
+    if (ctas > (int64_t)n_sm * per_sm) ctas = (int64_t)n_sm * per_sm;
+    if (ctas < 1) ctas = 1;
+    cossim2_candidates_kernel<NW, R><<<(unsigned)ctas, NW * 32, smem, st>>>(
+        row_pos, (const uint2 *)tl_ra, seg_f, seg_start, tile_nseg, n_tiles_left, n_left_rows, perm_a, bucket_ptr,
+        (const uint2 *)postings, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, n_right, perm_b,
+        thr_c, cand_row, cand_col, (unsigned long long)cand_cap, cand_count, queue);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+extern "C" {
+
+size_t sg_cossim2_smem_bytes(int warps_per_cta, int rows_per_tile, int tile_w) {
+    return k2_per_warp_bytes(rows_per_tile, tile_w) * warps_per_cta;
+}
+
+int sg_cossim2_candidates(const int64_t *row_pos, const void *tl_ra, const int32_t *seg_f, const int32_t *seg_start,
+                          const int32_t *tile_nseg, int64_t n_left_rows, const int32_t *perm_a,
+                          const int32_t *bucket_ptr, const void *postings, int64_t n_cols, int tile_w,
+                          int64_t tiles_per_group, int64_t n_right, const int32_t *perm_b, float cand_threshold,
+                          int32_t *cand_row, int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
+                          unsigned long long *queue, int warps_per_cta, int rows_per_tile, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_left_rows <= 0 || n_right <= 0) return SG_OK;
+    if (tile_w <= 0 || (tile_w & 31)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 32");
+    if (!(cand_threshold >= 0.f)) return fail(SG_ERR_INVALID, "cand_threshold must be >= 0");
+    int dev = 0, n_sm = 0;
+    SG_CUDA_TRY(cudaGetDevice(&dev));
+    SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+#define SG_CASE2(NW, R)                                                                                          \
+    if (warps_per_cta == NW && rows_per_tile == R)                                                               \
+        return launch_cossim2<NW, R>(row_pos, tl_ra, seg_f, seg_start, tile_nseg, n_left_rows, perm_a,           \
+                                     bucket_ptr, postings, n_cols, tile_w, tiles_per_group, n_right, perm_b,     \
+                                     cand_threshold, cand_row, cand_col, cand_cap, cand_count, queue, n_sm, st);
+    SG_CASE2(8, 4) SG_CASE2(8, 8) SG_CASE2(8, 16)
+    SG_CASE2(16, 4) SG_CASE2(16, 8) SG_CASE2(16, 16)
+    SG_CASE2(24, 4) SG_CASE2(24, 8)
+    SG_CASE2(32, 2) SG_CASE2(32, 4) SG_CASE2(32, 8)
+#undef SG_CASE2
+    return fail(SG_ERR_INVALID, "unsupported (warps_per_cta=%d, rows_per_tile=%d)", warps_per_cta, rows_per_tile);
 }
 
 }  // extern "C"

@@ -12,15 +12,16 @@ names = make_names(n, 0)
 t = time.time(); m, d, _ = P.tf_idf_matrices(names, dtype=np.float64); print("oracle tfidf %.2fs nnz=%d V=%d" % (time.time() - t, m.nnz, m.shape[1]))
 macs = P.hot_path_macs(m, m); print("MACs %.4g  (%.3f per pair)" % (macs, macs / n / n))
 A = D.DeviceCSR.from_scipy(m)
-cfgs = [(1536, 32), (3072, 16), (768, 32), (1024, 32), (2048, 24), (1536, 32)]
-if len(sys.argv) > 3:
-    cfgs = [(int(sys.argv[2]), int(sys.argv[3]))]
-for tile_w, warps in cfgs:
-    A._postings.clear()
+# (algo, tile_w, warps, rows_per_tile)
+cfgs = [(1, 1536, 32, 0), (2, 320, 16, 8), (2, 256, 16, 8), (2, 512, 16, 4), (2, 256, 32, 4), (2, 640, 8, 8), (2, 320, 16, 8)]
+if len(sys.argv) > 5:
+    cfgs = [(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))]
+for algo, tile_w, warps, rows in cfgs:
+    st = {"time_kernels": True}
     torch.cuda.synchronize(); t = time.time()
-    A.postings(tile_w); torch.cuda.synchronize(); tp = time.time() - t
-    st = {}
-    t = time.time(); got = D.cossim_topn(A, A, 20, 0.8, tile_w=tile_w, warps=warps, stats=st); torch.cuda.synchronize(); tk = time.time() - t
-    print("tile_w=%d warps=%d: postings %.1f ms, cossim_topn %.1f ms, cand=%d nnz=%d  -> %.3g MAC/s, %.1f GB/s algorithmic" % (
-        tile_w, warps, tp * 1e3, tk * 1e3, st["n_candidates"], got.nnz, macs / tk, 8 * macs / tk / 1e9))
+    got = D.cossim_topn(A, A, 20, 0.8, tile_w=tile_w, warps=warps, stats=st, algo=algo, rows_per_tile=rows or None)
+    torch.cuda.synchronize(); tk = time.time() - t
+    kms = sum(a.elapsed_time(b) for a, b in st["candidate_events"])
+    print("algo=%d tile_w=%d warps=%d rows=%d: cossim_topn %.1f ms (candidates kernel %.1f ms), cand=%d nnz=%d -> kernel %.3g MAC/s, %.0f GB/s algorithmic" % (
+        algo, tile_w, st["warps"], rows, tk * 1e3, kms, st["n_candidates"], got.nnz, macs / (kms / 1e3), 8 * macs / (kms / 1e3) / 1e9))
 t = time.time(); sym = D.symmetrize(got); torch.cuda.synchronize(); print("symmetrize %.1f ms nnz=%d" % ((time.time() - t) * 1e3, sym.nnz))
