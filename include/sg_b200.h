@@ -106,16 +106,18 @@ int sg_tfidf_vocab_keys(const int32_t *df_table /*[dev]*/, const int32_t *rank_t
 int64_t sg_num_tiles(int64_t n_right, int tile_w);
 
 /*
- * Right matrix -> tile-bucketed postings (the transpose that sp_matmul_topn
- * performs on `Bi.T`, sg.py:727/:738, done once and laid out for the kernel):
- * bucket (f, t) holds the (doc, weight) pairs of feature f whose doc lies in
- * column tile t; bucket_ptr has n_cols*T+1 entries; postings are 8 bytes
- * {int32 doc, float w}.
+ * Right matrix -> tile-major, column-sorted postings (the transpose that sp_matmul_topn performs on
+ * `Bi.T`, sg.py:727/:738, done once and laid out for the kernel).  The right rows are taken in the
+ * order `rank` (position of every row in heavy-feature signature order, sg_row_order; NULL = input
+ * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (t, f) = the docs of feature f
+ * inside tile t, sorted by position, at bucket_ptr[t*(n_cols+1)+f]; a posting is 8 bytes
+ * {int32 position - t*tile_w, float w}.  `indptr` may be a row-range view (indptr_base = indptr[0]).
  */
-size_t sg_postings_workspace_bytes(int64_t n_cols, int64_t n_tiles);
+size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr /*[dev]*/,
-                      const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/, int tile_w,
-                      int32_t *bucket_ptr /*[dev] n_cols*T+1*/, void *postings /*[dev] nnz*8 B*/,
+                      const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
+                      const int32_t *rank /*[dev] or NULL*/, int tile_w, int64_t indptr_base,
+                      int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/, void *postings /*[dev] nnz*8 B*/,
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
 /*
@@ -132,8 +134,11 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
  */
 int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
+                         const int32_t *perm_a /*[dev] processing order of the left rows, or NULL*/,
                          int64_t n_right, int64_t n_cols, const int32_t *bucket_ptr /*[dev]*/,
-                         const void *postings /*[dev]*/, int tile_w, float cand_threshold,
+                         const void *postings /*[dev]*/,
+                         const int32_t *perm_b /*[dev] position -> right row id, or NULL*/, int tile_w,
+                         float cand_threshold,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
                          int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
                          unsigned long long *cand_count /*[dev] 1*/,
@@ -181,13 +186,6 @@ int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, con
 int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
                  const int8_t *hrank, int32_t *perm /*[dev]*/, int32_t *rank /*[dev] or NULL*/, void *ws,
                  size_t ws_bytes, void *stream);
-/* right matrix -> tile-major, column-sorted postings; bucket (t, f) at bucket_ptr[t*(n_cols+1)+f];
- * `indptr` is the (possibly offset) row pointer of the n_rows right rows, indptr_base = indptr[0]. */
-size_t sg_postings2_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);
-int sg_postings2_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-                       const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
-                       int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/, void *postings /*[dev] nnz*8 B*/, void *ws,
-                       size_t ws_bytes, void *stream);
 /* left rows perm[0..n_rows) -> per-tile lists sorted by feature.  row_pos[n_rows+1]; tl_ra[nnz] {row, w};
  * seg_f / seg_start [nnz + n_tiles + 1] (tile t at row_pos[t*R] + t); tile_nseg[n_tiles]. */
 size_t sg_left_tiles_workspace_bytes(int64_t n_rows, int64_t nnz);

@@ -75,7 +75,6 @@ class DeviceCSR:
         self.dtype = np.dtype(dtype)
         self.norm_bound = float(norm_bound)
         self._host = None
-        self._postings = {}
         self._order = None          # (hrank, perm, rank) in heavy-feature signature order
         self._postings2 = {}
 
@@ -129,33 +128,9 @@ class DeviceCSR:
             raise AttributeError(name)
         return getattr(self.to_scipy(), name)
 
-    def postings(self, tile_w):
-        """(bucket_ptr, postings, T) of this matrix as the RIGHT operand, built once per tile width."""
-        if tile_w not in self._postings:
-            self._postings[tile_w] = build_postings(self, tile_w)
-        return self._postings[tile_w]
-
 
 def as_device_csr(m):
     return m if isinstance(m, DeviceCSR) else DeviceCSR.from_scipy(m)
-
-
-def build_postings(B, tile_w):
-    t = require_cuda()
-    L = _lib.load()
-    n_rows, n_cols = B.shape
-    T = int(L.sg_num_tiles(n_rows, tile_w))
-    nb = n_cols * T + 1
-    if nb >= 2**31 - 1:
-        raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
-    bucket_ptr = _empty(nb, t.int32, B.device)
-    post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
-    ws_bytes = int(L.sg_postings_workspace_bytes(n_cols, T))
-    ws = _empty(ws_bytes, t.uint8, B.device)
-    _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
-                                   tile_w, _ptr(bucket_ptr), _ptr(post), _ptr(ws), ws_bytes, _stream()))
-    LAUNCH_COUNTS["postings"] += 2
-    return bucket_ptr, post, T
 
 
 def heavy_features(B):
@@ -188,7 +163,7 @@ def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True):
     return perm, rank
 
 
-def right_side_v2(B, tile_w):
+def right_side(B, tile_w):
     """Signature order + tile-major column-sorted postings of the right matrix, cached on B."""
     t = require_cuda()
     L = _lib.load()
@@ -205,9 +180,9 @@ def right_side_v2(B, tile_w):
             raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
         bucket_ptr = _empty(nb, t.int32, B.device)
         post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
-        ws_bytes = int(L.sg_postings2_workspace_bytes(B.nnz, n_cols, T))
+        ws_bytes = int(L.sg_postings_workspace_bytes(B.nnz, n_cols, T))
         ws = _empty(ws_bytes, t.uint8, B.device)
-        _lib.check(L.sg_postings2_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
+        _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
                                         _ptr(rank), tile_w, B.base, _ptr(bucket_ptr), _ptr(post), _ptr(ws), ws_bytes,
                                         _stream()))
         LAUNCH_COUNTS["postings"] += 2
@@ -330,18 +305,19 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         _lib.check(L.sg_device_info(None, ctypes.byref(smem_optin), None))
         while warps > 8 and int(L.sg_cossim2_smem_bytes(warps, rows_per_tile, tile_w)) > smem_optin.value:
             warps -= 8
-        hrank, perm_b, rank_b, bucket_ptr, post, T = right_side_v2(B, tile_w)
-        if A is B and row_begin == 0 and row_end == n_left:
-            perm_a = perm_b
-        else:
-            perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
-        row_pos, tl_ra, seg_f, seg_start, tile_nseg = left_tiles_v2(A, perm_a, n_rows, rows_per_tile)
-        tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
     else:
         tile_w, warps = pick_tile(n_right, tile_w, warps)
-        bucket_ptr, post, T = B.postings(tile_w)
-        # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
-        tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
+    # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
+    # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
+    hrank, perm_b, rank_b, bucket_ptr, post, T = right_side(B, tile_w)
+    if A is B and row_begin == 0 and row_end == n_left:
+        perm_a = perm_b
+    else:
+        perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
+    if algo == 2:
+        row_pos, tl_ra, seg_f, seg_start, tile_nseg = left_tiles_v2(A, perm_a, n_rows, rows_per_tile)
+    # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
+    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
     for attempt in range(3):
         cand_row = _empty(cap, t.int32, dev)
         cand_col = _empty(cap, t.int32, dev)
@@ -358,9 +334,9 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                 _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, rows_per_tile, _stream()))
         else:
             _lib.check(L.sg_cossim_candidates(
-                _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, n_right, A.shape[1],
-                _ptr(bucket_ptr), _ptr(post), tile_w, thr_c, tiles_per_group, _ptr(cand_row), _ptr(cand_col), cap,
-                c_count, c_queue, warps, _stream()))
+                _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, _ptr(perm_a), n_right,
+                A.shape[1], _ptr(bucket_ptr), _ptr(post), _ptr(perm_b), tile_w, thr_c, tiles_per_group,
+                _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
         if stats is not None and stats.get("time_kernels"):
             ev1.record()

@@ -17,32 +17,32 @@
 namespace sg {
 
 // ---------------------------------------------------------------------------
-// postings build
+// postings build: tile-major, column-sorted, in signature order of the right rows
 // ---------------------------------------------------------------------------
-__global__ void postings_hist_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
-                                     const int32_t *__restrict__ indices, int tile_w, int64_t T,
+// key = (bucket << 16) | local column, bucket = t * (n_cols + 1) + f, t = rank[doc] / tile_w
+__global__ void postings_keys_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
+                                     const int32_t *__restrict__ indices, const float *__restrict__ val,
+                                     const int32_t *__restrict__ rank, int W, int64_t V1, int64_t base,
+                                     uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                      int32_t *__restrict__ cnt) {
-    // one warp per right row: lanes stride over the row's entries
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
-    const int64_t t = row / tile_w;
-    const int64_t p1 = indptr[row + 1];
-    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32)
-        atomicAdd(&cnt[(int64_t)indices[p] * T + t], 1);
-}
-
-__global__ void postings_scatter_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
-                                        const int32_t *__restrict__ indices,
-                                        const float *__restrict__ val, int tile_w, int64_t T,
-                                        int32_t *__restrict__ cursor, uint2 *__restrict__ post) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int64_t t = row / tile_w;
+    const int64_t pos = rank ? rank[row] : row;
+    const int64_t t = pos / W;
+    const uint64_t local = (uint64_t)(pos - t * W);
     const int64_t p1 = indptr[row + 1];
     for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32) {
-        const int32_t pos = atomicAdd(&cursor[(int64_t)indices[p] * T + t], 1);
-        post[pos] = make_uint2((uint32_t)row, __float_as_uint(val[p]));
+        const int64_t b = t * V1 + indices[p];
+        keys[p - base] = ((uint64_t)b << 16) | local;
+        vals[p - base] = __float_as_uint(val[p]);
+        atomicAdd(cnt + b, 1);
     }
+}
+
+__global__ void postings_pack_kernel(int64_t nnz, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                     uint2 *__restrict__ post) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) post[i] = make_uint2((uint32_t)(keys[i] & 0xffffu), vals[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -54,8 +54,9 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                          const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
-                         int64_t n_right, const int32_t *__restrict__ bptr,
-                         const uint2 *__restrict__ post, int W, int64_t T, int64_t tiles_per_group, float thr_c,
+                         const int32_t *__restrict__ perm_a, int64_t n_right, const int32_t *__restrict__ bptr,
+                         const uint2 *__restrict__ post, const int32_t *__restrict__ perm_b, int64_t V1, int W,
+                         int64_t T, int64_t tiles_per_group, float thr_c,
                          int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
                          unsigned long long cap, unsigned long long *__restrict__ cand_count,
                          unsigned long long *__restrict__ row_queue) {
@@ -79,7 +80,8 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         item = __shfl_sync(FULL, item, 0);
         if (item >= n_items) break;
         const int64_t group = (int64_t)(item / (unsigned long long)n_rows);
-        const int64_t row = row_begin + (int64_t)(item % (unsigned long long)n_rows);
+        const int64_t ridx = (int64_t)(item % (unsigned long long)n_rows);
+        const int64_t row = perm_a ? perm_a[ridx] : row_begin + ridx;   // signature order: neighbours share buckets
         const int64_t p0 = a_indptr[row];
         const int nf = (int)(a_indptr[row + 1] - p0);
         if (nf == 0) continue;
@@ -87,17 +89,17 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         const int64_t t_end = t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T;
 
         for (int64_t t = t_begin; t < t_end; ++t) {
-            const int c0 = (int)(t * W);
+            const int64_t c0 = t * W;
+            const int32_t *bp = bptr + t * V1;
             for (int base = 0; base < nf; base += 32) {
                 const int k = base + lane;
                 int b0 = 0, b1 = 0;
                 float a = 0.f;
                 if (k < nf) {
-                    const int64_t f = a_idx[p0 + k];
+                    const int f = a_idx[p0 + k];
                     a = a_val[p0 + k];
-                    const int32_t *bp = bptr + f * T + t;
-                    b0 = bp[0];
-                    b1 = bp[1];
+                    b0 = bp[f];
+                    b1 = bp[f + 1];
                 }
                 const int len = b1 - b0;
                 // short buckets: every lane walks its own bucket (one L2 latency for all of them);
@@ -105,7 +107,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                 if (len > 0 && len <= SHORT_BUCKET) {
                     for (int j = 0; j < len; ++j) {
                         const uint2 e = post[b0 + j];
-                        atomicAdd(acc + ((int)e.x - c0), a * __uint_as_float(e.y));
+                        atomicAdd(acc + e.x, a * __uint_as_float(e.y));
                     }
                 }
                 __syncwarp();
@@ -121,14 +123,14 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     int p = s + lane;
                     for (; p + 96 < e; p += 128) {
                         const uint2 e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-                        acc[(int)e0.x - c0] += ak * __uint_as_float(e0.y);
-                        acc[(int)e1.x - c0] += ak * __uint_as_float(e1.y);
-                        acc[(int)e2.x - c0] += ak * __uint_as_float(e2.y);
-                        acc[(int)e3.x - c0] += ak * __uint_as_float(e3.y);
+                        acc[e0.x] += ak * __uint_as_float(e0.y);
+                        acc[e1.x] += ak * __uint_as_float(e1.y);
+                        acc[e2.x] += ak * __uint_as_float(e2.y);
+                        acc[e3.x] += ak * __uint_as_float(e3.y);
                     }
                     for (; p < e; p += 32) {
                         const uint2 e0 = post[p];
-                        acc[(int)e0.x - c0] += ak * __uint_as_float(e0.y);
+                        acc[e0.x] += ak * __uint_as_float(e0.y);
                     }
                     __syncwarp();
                 }
@@ -150,7 +152,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                                 const unsigned long long slot = atomicAdd(cand_count, 1ull);
                                 if (slot < cap) {
                                     cand_row[slot] = (int32_t)row;
-                                    cand_col[slot] = c0 + c + i;
+                                    cand_col[slot] = perm_b ? perm_b[c0 + c + i] : (int32_t)(c0 + c + i);
                                 }
                             }
                         }
@@ -338,43 +340,55 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w) {
     return t < 1 ? 1 : t;
 }
 
-size_t sg_postings_workspace_bytes(int64_t n_cols, int64_t n_tiles) {
-    const size_t nb = (size_t)n_cols * (size_t)n_tiles + 1;
-    size_t cub_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (int32_t *)nullptr, (int64_t)nb);
-    return align_up(nb * sizeof(int32_t), 256) + align_up(cub_bytes, 256) + 1024;
+size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles) {
+    const int64_t nb = n_tiles * (n_cols + 1) + 1;
+    const int64_t n = nnz < 1 ? 1 : nnz;
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t *)nullptr, (int32_t *)nullptr, nb);
+    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + align_up((size_t)nb * 4, 256) +
+           align_up(b1 > b2 ? b1 : b2, 256) + 4096;
 }
 
-int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr,
-                      const int32_t *indices, const float *val32, int tile_w, int32_t *bucket_ptr,
-                      void *postings, void *ws, size_t ws_bytes, void *stream_) {
+int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
+                      const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
+                      int32_t *bucket_ptr, void *postings, void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (tile_w <= 0 || (tile_w & 127)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 128");
-    if (nnz >= (int64_t)0x7fffffff) return fail(SG_ERR_OVERFLOW, "right matrix nnz %lld does not fit int32 postings", (long long)nnz);
+    if (tile_w <= 0 || (tile_w & 31) || tile_w > 65535)
+        return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 below 65536");
+    if (nnz >= (int64_t)0x7fffffff)
+        return fail(SG_ERR_OVERFLOW, "right matrix nnz %lld does not fit int32 postings", (long long)nnz);
     const int64_t T = sg_num_tiles(n_rows, tile_w);
-    const int64_t nb = n_cols * T + 1;
+    const int64_t V1 = n_cols + 1;
+    const int64_t nb = T * V1 + 1;
     if (nb >= (int64_t)0x7fffffff) return fail(SG_ERR_OVERFLOW, "bucket table %lld too large", (long long)nb);
     Arena ar(ws, ws_bytes);
-    int32_t *cursor = ar.take<int32_t>((size_t)nb);
-    size_t cub_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (int32_t *)nullptr, nb);
-    char *cub_tmp = ar.take<char>(cub_bytes);
+    const size_t n = (size_t)(nnz < 1 ? 1 : nnz);
+    uint64_t *keys = ar.take<uint64_t>(n);
+    uint64_t *keys_sorted = ar.take<uint64_t>(n);
+    uint32_t *vals = ar.take<uint32_t>(n);
+    uint32_t *vals_sorted = ar.take<uint32_t>(n);
+    int32_t *cnt = ar.take<int32_t>((size_t)nb);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_sorted, vals, vals_sorted, (int64_t)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, cnt, bucket_ptr, nb);
+    size_t cub_bytes = b1 > b2 ? b1 : b2;
+    char *tmp = ar.take<char>(cub_bytes);
     if (!ar.ok()) return fail(SG_ERR_INVALID, "postings workspace too small (%zu < %zu)", ws_bytes, ar.off);
-
-    SG_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(int32_t), st));
-    if (n_rows > 0) {
-        const int wpb = 8;
-        const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
-        postings_hist_kernel<<<grid, wpb * 32, 0, st>>>(n_rows, indptr, indices, tile_w, T, cursor);
+    SG_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nb * 4, st));
+    if (n_rows > 0 && nnz > 0) {
+        postings_keys_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, val32, rank, tile_w,
+                                                                         V1, indptr_base, keys, vals, cnt);
         SG_LAUNCH_CHECK();
     }
-    SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursor, bucket_ptr, nb, st));
-    SG_CUDA_TRY(cudaMemcpyAsync(cursor, bucket_ptr, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    if (n_rows > 0) {
-        const int wpb = 8;
-        const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
-        postings_scatter_kernel<<<grid, wpb * 32, 0, st>>>(n_rows, indptr, indices, val32, tile_w, T, cursor,
-                                                           (uint2 *)postings);
+    SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, cnt, bucket_ptr, nb, st));
+    if (nnz > 0) {
+        const int bits = 16 + bits_for((uint64_t)(nb - 1));
+        SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, nnz, 0,
+                                                    bits > 64 ? 64 : bits, st));
+        postings_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted,
+                                                                            (uint2 *)postings);
         SG_LAUNCH_CHECK();
     }
     return SG_OK;
@@ -384,8 +398,9 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 
 template <int NW>
 static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
-                             int64_t row_begin, int64_t row_end, int64_t n_right,
-                             const int32_t *bucket_ptr, const void *postings, int tile_w, int64_t tiles_per_group,
+                             int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
+                             int64_t n_cols, const int32_t *bucket_ptr, const void *postings,
+                             const int32_t *perm_b, int tile_w, int64_t tiles_per_group,
                              float thr_c, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                              unsigned long long *cand_count, unsigned long long *row_queue, int n_sm,
                              cudaStream_t st) {
@@ -400,8 +415,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, 
     if (ctas > (int64_t)n_sm * per_sm) ctas = (int64_t)n_sm * per_sm;   // persistent grid: resident CTAs x SMs
     if (ctas < 1) ctas = 1;
     cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
-        a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr, (const uint2 *)postings, tile_w, T,
-        tiles_per_group < 1 ? 1 : tiles_per_group, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
+        a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right, bucket_ptr, (const uint2 *)postings,
+        perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
         cand_count, row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
@@ -410,12 +425,12 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, 
 extern "C" {
 
 int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
-                         int64_t row_begin, int64_t row_end, int64_t n_right, int64_t n_cols,
-                         const int32_t *bucket_ptr, const void *postings, int tile_w, float cand_threshold,
+                         int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
+                         int64_t n_cols, const int32_t *bucket_ptr, const void *postings, const int32_t *perm_b,
+                         int tile_w, float cand_threshold,
                          int64_t tiles_per_group, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                          unsigned long long *cand_count, unsigned long long *row_queue, int warps_per_cta,
                          void *stream_) {
-    (void)n_cols;
     cudaStream_t st = (cudaStream_t)stream_;
     if (row_end <= row_begin || n_right <= 0) return SG_OK;
     if (tile_w <= 0 || (tile_w & 127)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 128");
@@ -429,9 +444,10 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, cons
                     (size_t)warps_per_cta * tile_w * sizeof(float), smem_optin);
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
-        return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, n_right, bucket_ptr,  \
-                                     postings, tile_w, tiles_per_group, cand_threshold, cand_row, cand_col,  \
-                                     cand_cap, cand_count, row_queue, n_sm, st);
+        return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right,     \
+                                     n_cols, bucket_ptr, postings, perm_b, tile_w, tiles_per_group,          \
+                                     cand_threshold, cand_row, cand_col, cand_cap, cand_count, row_queue,    \
+                                     n_sm, st);
     switch (warps_per_cta) {
         SG_CASE(4)
         SG_CASE(8)

@@ -29,34 +29,6 @@ __host__ __device__ constexpr size_t k2_per_warp_bytes(int R, int Wc) {
 }
 
 // ---------------------------------------------------------------------------
-// postings, tile-major, column-sorted
-// ---------------------------------------------------------------------------
-__global__ void postings2_keys_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
-                                      const int32_t *__restrict__ indices, const float *__restrict__ val,
-                                      const int32_t *__restrict__ rank, int Wc, int64_t V1, int64_t base,
-                                      uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                      int32_t *__restrict__ cnt) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int64_t pos = rank[row];
-    const int64_t t = pos / Wc;
-    const uint64_t local = (uint64_t)(pos - t * Wc);
-    const int64_t p1 = indptr[row + 1];
-    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32) {
-        const int64_t b = t * V1 + indices[p];
-        keys[p - base] = ((uint64_t)b << 16) | local;
-        vals[p - base] = __float_as_uint(val[p]);
-        atomicAdd(cnt + b, 1);
-    }
-}
-
-__global__ void postings2_pack_kernel(int64_t nnz, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                      uint2 *__restrict__ post) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) post[i] = make_uint2((uint32_t)(keys[i] & 0xffffu), vals[i]);
-}
-
-// ---------------------------------------------------------------------------
 // left tile lists
 // ---------------------------------------------------------------------------
 __global__ void tiles_rowlen_kernel(int64_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ perm,
@@ -343,64 +315,6 @@ cossim2_candidates_kernel(const int64_t *__restrict__ tile_ptr, const uint2 *__r
 using namespace sg;
 
 extern "C" {
-
-size_t sg_postings2_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles) {
-    const int64_t nb = n_tiles * (n_cols + 1) + 1;
-    const int64_t n = nnz < 1 ? 1 : nnz;
-    size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, n);
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t *)nullptr, (int32_t *)nullptr, nb);
-    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + align_up((size_t)nb * 4, 256) +
-           align_up(b1 > b2 ? b1 : b2, 256) + 4096;
-}
-
-// Right matrix rows [0, n_rows) with absolute indptr (first stored value at indptr[0]); `rank` = position of each
-// row in signature order.  bucket_ptr: n_tiles*(n_cols+1)+1 int32, bucket (t, f) at index t*(n_cols+1)+f.
-int sg_postings2_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-                       const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
-                       int32_t *bucket_ptr, void *postings, void *ws, size_t ws_bytes, void *stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
-    if (tile_w <= 0 || (tile_w & 31) || tile_w > 65535) return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 below 65536");
-    if (nnz >= (int64_t)0x7fffffff) return fail(SG_ERR_OVERFLOW, "right matrix nnz %lld does not fit int32 postings", (long long)nnz);
-    const int64_t T = sg_num_tiles(n_rows, tile_w);
-    const int64_t V1 = n_cols + 1;
-    const int64_t nb = T * V1 + 1;
-    if (nb >= ((int64_t)1 << 47) || nb >= (int64_t)0x7fffffff)
-        return fail(SG_ERR_OVERFLOW, "bucket table %lld too large", (long long)nb);
-    Arena ar(ws, ws_bytes);
-    const size_t n = (size_t)(nnz < 1 ? 1 : nnz);
-    uint64_t *keys = ar.take<uint64_t>(n);
-    uint64_t *keys_sorted = ar.take<uint64_t>(n);
-    uint32_t *vals = ar.take<uint32_t>(n);
-    uint32_t *vals_sorted = ar.take<uint32_t>(n);
-    int32_t *cnt = ar.take<int32_t>((size_t)nb);
-    size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_sorted, vals, vals_sorted, (int64_t)n);
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, cnt, bucket_ptr, nb);
-    size_t cub_bytes = b1 > b2 ? b1 : b2;
-    char *tmp = ar.take<char>(cub_bytes);
-    if (!ar.ok()) return fail(SG_ERR_INVALID, "postings2 workspace too small (%zu < %zu)", ws_bytes, ar.off);
-    SG_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nb * 4, st));
-    if (n_rows > 0 && nnz > 0) {
-        postings2_keys_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, val32, rank, tile_w,
-                                                                          V1, indptr_base, keys, vals, cnt);
-        SG_LAUNCH_CHECK();
-    }
-    SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, cnt, bucket_ptr, nb, st));
-    if (nnz > 0) {
-        int bits = 16, hb = 0;
-        uint64_t top = (uint64_t)(nb - 1);
-        while (top) { ++hb; top >>= 1; }
-        bits += hb < 1 ? 1 : hb;
-        SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, nnz, 0,
-                                                    bits > 64 ? 64 : bits, st));
-        postings2_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted,
-                                                                             (uint2 *)postings);
-        SG_LAUNCH_CHECK();
-    }
-    return SG_OK;
-}
 
 size_t sg_left_tiles_workspace_bytes(int64_t n_rows, int64_t nnz) {
     size_t b = 0;
