@@ -111,13 +111,16 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w);
  * order `rank` (position of every row in heavy-feature signature order, sg_row_order; NULL = input
  * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (t, f) = the docs of feature f
  * inside tile t, sorted by position, at bucket_ptr[t*(n_cols+1)+f]; a posting is 8 bytes
- * {int32 position - t*tile_w, float w}.  `indptr` may be a row-range view (indptr_base = indptr[0]).
+ * {int32 position - t*tile_w, float w}.  `bucket_dir` (optional) receives the same directory as aligned
+ * {int32 start, int32 length} pairs, T*(n_cols+1) of them, the form sg_cossim_candidates reads.
+ * `indptr` may be a row-range view (indptr_base = indptr[0]).
  */
 size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr /*[dev]*/,
                       const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
                       const int32_t *rank /*[dev] or NULL*/, int tile_w, int64_t indptr_base,
-                      int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/, void *postings /*[dev] nnz*8 B*/,
+                      int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/,
+                      void *bucket_dir /*[dev] T*(n_cols+1)*8 B or NULL*/, void *postings /*[dev] nnz*8 B*/,
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
 /*
@@ -135,7 +138,7 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
                          const int32_t *perm_a /*[dev] processing order of the left rows, or NULL*/,
-                         int64_t n_right, int64_t n_cols, const int32_t *bucket_ptr /*[dev]*/,
+                         int64_t n_right, int64_t n_cols, const void *bucket_dir /*[dev] {start,len} pairs*/,
                          const void *postings /*[dev]*/,
                          const int32_t *perm_b /*[dev] position -> right row id, or NULL*/, int tile_w,
                          float cand_threshold,

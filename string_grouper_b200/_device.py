@@ -16,7 +16,7 @@ _TORCH = None
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0, "order": 0, "tiles": 0}
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "1536"))
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "768"))
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 K2_ALGO = int(os.environ.get("SG_B200_K2", "1"))            # 1 = row-wise (default), 2 = experimental tiled formulation
@@ -179,14 +179,15 @@ def right_side(B, tile_w):
         if nb >= 2**31 - 1:
             raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
         bucket_ptr = _empty(nb, t.int32, B.device)
+        bucket_dir = _empty(2 * nb, t.int32, B.device)
         post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
         ws_bytes = int(L.sg_postings_workspace_bytes(B.nnz, n_cols, T))
         ws = _empty(ws_bytes, t.uint8, B.device)
         _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
-                                        _ptr(rank), tile_w, B.base, _ptr(bucket_ptr), _ptr(post), _ptr(ws), ws_bytes,
-                                        _stream()))
-        LAUNCH_COUNTS["postings"] += 2
-        B._postings2[tile_w] = (bucket_ptr, post, T)
+                                       _ptr(rank), tile_w, B.base, _ptr(bucket_ptr), _ptr(bucket_dir), _ptr(post),
+                                       _ptr(ws), ws_bytes, _stream()))
+        LAUNCH_COUNTS["postings"] += 3
+        B._postings2[tile_w] = (bucket_ptr, bucket_dir, post, T)
     return (hrank, perm, rank) + B._postings2[tile_w]
 
 
@@ -309,7 +310,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         tile_w, warps = pick_tile(n_right, tile_w, warps)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
-    hrank, perm_b, rank_b, bucket_ptr, post, T = right_side(B, tile_w)
+    hrank, perm_b, rank_b, bucket_ptr, bucket_dir, post, T = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:
@@ -335,7 +336,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         else:
             _lib.check(L.sg_cossim_candidates(
                 _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, _ptr(perm_a), n_right,
-                A.shape[1], _ptr(bucket_ptr), _ptr(post), _ptr(perm_b), tile_w, thr_c, tiles_per_group,
+                A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, thr_c, tiles_per_group,
                 _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
         if stats is not None and stats.get("time_kernels"):

@@ -45,16 +45,26 @@ __global__ void postings_pack_kernel(int64_t nnz, const uint64_t *__restrict__ k
     if (i < nnz) post[i] = make_uint2((uint32_t)(keys[i] & 0xffffu), vals[i]);
 }
 
+// bucket directory: one aligned 8-byte {start, length} per (tile, feature) so that a lane fetches it in one load
+__global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr, int2 *__restrict__ dir) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb) dir[i] = make_int2(ptr[i], ptr[i + 1] - ptr[i]);
+}
+
 // ---------------------------------------------------------------------------
 // candidate generation
 // ---------------------------------------------------------------------------
 constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-privately
 
+// The kernel is latency-bound on L2 posting reads: 64 resident warps per SM (32 registers per thread)
+// beat deeper per-warp prefetching at 40-48 registers (measured, profiles/r1_notes.md).
+constexpr int min_ctas(int nw) { return 64 / nw < 1 ? 1 : 64 / nw; }
+
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, min_ctas(NW))
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                          const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
-                         const int32_t *__restrict__ perm_a, int64_t n_right, const int32_t *__restrict__ bptr,
+                         const int32_t *__restrict__ perm_a, int64_t n_right, const int2 *__restrict__ bdir,
                          const uint2 *__restrict__ post, const int32_t *__restrict__ perm_b, int64_t V1, int W,
                          int64_t T, int64_t tiles_per_group, float thr_c,
                          int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
@@ -90,24 +100,27 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
 
         for (int64_t t = t_begin; t < t_end; ++t) {
             const int64_t c0 = t * W;
-            const int32_t *bp = bptr + t * V1;
+            const int2 *bd = bdir + t * V1;
+            float seen = 0.f;      // largest value this lane wrote into the tile (scores are sums of products >= 0)
             for (int base = 0; base < nf; base += 32) {
                 const int k = base + lane;
-                int b0 = 0, b1 = 0;
+                int b0 = 0, len = 0;
                 float a = 0.f;
                 if (k < nf) {
                     const int f = a_idx[p0 + k];
                     a = a_val[p0 + k];
-                    b0 = bp[f];
-                    b1 = bp[f + 1];
+                    const int2 d = bd[f];
+                    b0 = d.x;
+                    len = d.y;
                 }
-                const int len = b1 - b0;
+                const int b1 = b0 + len;
                 // short buckets: every lane walks its own bucket (one L2 latency for all of them);
                 // two lanes may meet on one column, hence the shared-memory atomic.
                 if (len > 0 && len <= SHORT_BUCKET) {
                     for (int j = 0; j < len; ++j) {
                         const uint2 e = post[b0 + j];
-                        atomicAdd(acc + e.x, a * __uint_as_float(e.y));
+                        const float x = a * __uint_as_float(e.y);
+                        seen = fmaxf(seen, atomicAdd(acc + e.x, x) + x);
                     }
                 }
                 __syncwarp();
@@ -123,17 +136,32 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     int p = s + lane;
                     for (; p + 96 < e; p += 128) {
                         const uint2 e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-                        acc[e0.x] += ak * __uint_as_float(e0.y);
-                        acc[e1.x] += ak * __uint_as_float(e1.y);
-                        acc[e2.x] += ak * __uint_as_float(e2.y);
-                        acc[e3.x] += ak * __uint_as_float(e3.y);
+                        const float v0 = fmaf(ak, __uint_as_float(e0.y), acc[e0.x]);
+                        acc[e0.x] = v0;
+                        const float v1 = fmaf(ak, __uint_as_float(e1.y), acc[e1.x]);
+                        acc[e1.x] = v1;
+                        const float v2 = fmaf(ak, __uint_as_float(e2.y), acc[e2.x]);
+                        acc[e2.x] = v2;
+                        const float v3 = fmaf(ak, __uint_as_float(e3.y), acc[e3.x]);
+                        acc[e3.x] = v3;
+                        seen = fmaxf(fmaxf(fmaxf(seen, v0), fmaxf(v1, v2)), v3);
                     }
                     for (; p < e; p += 32) {
                         const uint2 e0 = post[p];
-                        acc[e0.x] += ak * __uint_as_float(e0.y);
+                        const float v0 = fmaf(ak, __uint_as_float(e0.y), acc[e0.x]);
+                        acc[e0.x] = v0;
+                        seen = fmaxf(seen, v0);
                     }
                     __syncwarp();
                 }
+            }
+            // No value written into this tile exceeded the candidate threshold (the common case):
+            // clearing is enough, the tile need not be read back.
+            if (!__any_sync(FULL, seen > thr_c)) {
+                for (int c = lane * 4; c < W; c += 128)
+                    *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                continue;
             }
             // sweep: report scores above the candidate threshold, clear the tile
             for (int c = lane * 4; c < W; c += 128) {
@@ -353,7 +381,8 @@ size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles)
 
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
                       const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
-                      int32_t *bucket_ptr, void *postings, void *ws, size_t ws_bytes, void *stream_) {
+                      int32_t *bucket_ptr, void *bucket_dir, void *postings, void *ws, size_t ws_bytes,
+                      void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (tile_w <= 0 || (tile_w & 31) || tile_w > 65535)
         return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 below 65536");
@@ -383,6 +412,10 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
         SG_LAUNCH_CHECK();
     }
     SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, cnt, bucket_ptr, nb, st));
+    if (bucket_dir) {
+        postings_dir_kernel<<<(unsigned)((nb - 1 + 255) / 256), 256, 0, st>>>(nb - 1, bucket_ptr, (int2 *)bucket_dir);
+        SG_LAUNCH_CHECK();
+    }
     if (nnz > 0) {
         const int bits = 16 + bits_for((uint64_t)(nb - 1));
         SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, nnz, 0,
@@ -399,7 +432,7 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 template <int NW>
 static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                              int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
-                             int64_t n_cols, const int32_t *bucket_ptr, const void *postings,
+                             int64_t n_cols, const void *bucket_dir, const void *postings,
                              const int32_t *perm_b, int tile_w, int64_t tiles_per_group,
                              float thr_c, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                              unsigned long long *cand_count, unsigned long long *row_queue, int n_sm,
@@ -415,7 +448,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, 
     if (ctas > (int64_t)n_sm * per_sm) ctas = (int64_t)n_sm * per_sm;   // persistent grid: resident CTAs x SMs
     if (ctas < 1) ctas = 1;
     cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
-        a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right, bucket_ptr, (const uint2 *)postings,
+        a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
+        (const uint2 *)postings,
         perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
         cand_count, row_queue);
     SG_LAUNCH_CHECK();
@@ -426,7 +460,7 @@ extern "C" {
 
 int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                          int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
-                         int64_t n_cols, const int32_t *bucket_ptr, const void *postings, const int32_t *perm_b,
+                         int64_t n_cols, const void *bucket_dir, const void *postings, const int32_t *perm_b,
                          int tile_w, float cand_threshold,
                          int64_t tiles_per_group, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                          unsigned long long *cand_count, unsigned long long *row_queue, int warps_per_cta,
@@ -445,7 +479,7 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, cons
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
         return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right,     \
-                                     n_cols, bucket_ptr, postings, perm_b, tile_w, tiles_per_group,          \
+                                     n_cols, bucket_dir, postings, perm_b, tile_w, tiles_per_group,          \
                                      cand_threshold, cand_row, cand_col, cand_cap, cand_count, row_queue,    \
                                      n_sm, st);
     switch (warps_per_cta) {

@@ -13,7 +13,7 @@ t = time.time(); m, d, _ = P.tf_idf_matrices(names, dtype=np.float64); print("or
 macs = P.hot_path_macs(m, m); print("MACs %.4g  (%.3f per pair)" % (macs, macs / n / n))
 A = D.DeviceCSR.from_scipy(m)
 # (algo, tile_w, warps, rows_per_tile)
-cfgs = [(1, 1536, 32, 0), (2, 320, 16, 8), (2, 256, 16, 8), (2, 512, 16, 4), (2, 256, 32, 4), (2, 640, 8, 8), (2, 320, 16, 8)]
+cfgs = [(1, 768, 32, 0), (1, 896, 32, 0), (1, 1536, 32, 0), (1, 768, 32, 0)]
 if len(sys.argv) > 5:
     cfgs = [(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))]
 for algo, tile_w, warps, rows in cfgs:

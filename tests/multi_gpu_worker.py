@@ -1,0 +1,27 @@
+"""Worker for tests/test_multi_gpu.py: run under torchrun, one rank per GPU (NCCL)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pandas as pd
+import torch
+import torch.distributed as dist
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import string_grouper_b200 as api
+from synth_corpus import make_names
+
+out = sys.argv[1]
+names = pd.Series(make_names(30011, seed=91))
+dupes = pd.Series(make_names(7000, seed=92) + make_names(30011, seed=91)[:999])
+a = api.match_strings(names, min_similarity=0.8)
+b = api.match_strings(names, dupes, min_similarity=0.7, max_n_matches=5)
+g = api.group_similar_strings(names)
+a.to_pickle("%s.self.%d.pkl" % (out, rank))
+b.to_pickle("%s.two.%d.pkl" % (out, rank))
+g.to_pickle("%s.grp.%d.pkl" % (out, rank))
+dist.barrier()
+dist.destroy_process_group()
