@@ -287,7 +287,7 @@ def main():
     achieved = alg_bytes / (k2_ms / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:      # the ncu capture is a 1-GPU launch over all rows
         traffic = json.load(open(tpath)).get("%d" % n)
     roofline = {"bound": "hbm", "kernel": "sg::cossim_candidates_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

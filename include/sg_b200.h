@@ -83,7 +83,10 @@ int sg_tfidf_count(const uint8_t *bytes /*[dev]*/, const int64_t *offsets /*[dev
  * bound of nnz), so no host read-back is needed between the two phases.
  */
 size_t sg_tfidf_finalize_workspace_bytes(int64_t n_docs, int ngram);
-int sg_tfidf_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs, int ngram, int dtype,
+int sg_tfidf_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs,
+                      int64_t n_docs_fit /* documents counted in df_table: n_docs, or the global count when the
+                                            corpus is sharded over GPUs and df_table was all-reduced */,
+                      int ngram, int dtype,
                       const int32_t *df_table /*[dev]*/, int32_t *rank_table /*[dev] slots*/,
                       const uint32_t *scratch_key, const uint32_t *scratch_tf, int32_t *row_nnz,
                       int64_t *indptr /*[dev] n_docs+1*/, int32_t *indices /*[dev]*/,

@@ -462,15 +462,17 @@ def upload_strings(data, offsets, device=None):
     return d_bytes, d_off, total
 
 
-def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None):
+def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None, df_allreduce=None, n_docs_fit=None):
     """K1 from host buffers: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM."""
     d_bytes, d_off, total = upload_strings(data, offsets, device)
     if stats is not None:
         stats["h2d_bytes"] = int(total + 8 * len(offsets))
-    return tfidf_resident(d_bytes, d_off, len(offsets) - 1, total, n_master, ngram, flags, dtype, stats=stats)
+    return tfidf_resident(d_bytes, d_off, len(offsets) - 1, total, n_master, ngram, flags, dtype, stats=stats,
+                          df_allreduce=df_allreduce, n_docs_fit=n_docs_fit)
 
 
-def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype, stats=None):
+def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype, stats=None, df_allreduce=None,
+                   n_docs_fit=None):
     """K1 on strings already resident in HBM.
 
     Device counterpart of _fit_vectorizer + transform (string_grouper.py:685-707): the vocabulary /
@@ -493,6 +495,8 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
     row_nnz = _empty(n_docs + 1, t.int32, device)
     _lib.check(L.sg_tfidf_count(_ptr(d_bytes), _ptr(d_off), n_docs, int(ngram), int(flags), _ptr(df), _ptr(s_clean),
                                 _ptr(s_sort), _ptr(s_key), _ptr(s_tf), _ptr(row_nnz), _stream()))
+    if df_allreduce is not None:
+        df_allreduce(df)          # corpus sharded over GPUs: document frequencies are summed over the ranks (NCCL)
     indptr = _empty(n_docs + 1, t.int64, device)
     indices = _empty(total, t.int32, device)
     val32 = _empty(total, t.float32, device)
@@ -501,7 +505,8 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
     ws_bytes = int(L.sg_tfidf_finalize_workspace_bytes(n_docs, int(ngram)))
     ws = _empty(ws_bytes, t.uint8, device)
     dt = _lib.SG_DTYPE_F32 if np_dtype == np.float32 else _lib.SG_DTYPE_F64
-    _lib.check(L.sg_tfidf_finalize(_ptr(d_off), n_docs, int(ngram), dt, _ptr(df), _ptr(rank), _ptr(s_key), _ptr(s_tf),
+    _lib.check(L.sg_tfidf_finalize(_ptr(d_off), n_docs, int(n_docs if n_docs_fit is None else n_docs_fit), int(ngram),
+                                   dt, _ptr(df), _ptr(rank), _ptr(s_key), _ptr(s_tf),
                                    _ptr(row_nnz), _ptr(indptr), _ptr(indices), _ptr(val64), _ptr(val32),
                                    ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
                                    ws_bytes, _stream()))
@@ -512,7 +517,7 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
     nnz = int(head[1])
     split = int(head[2])
     val = val64 if np_dtype == np.float64 else val32
-    vocab = DeviceVocabulary(df, rank, ngram, n_docs, V)
+    vocab = DeviceVocabulary(df, rank, ngram, n_docs if n_docs_fit is None else n_docs_fit, V)
     if stats is not None:
         stats.update(n_docs=n_docs, total_bytes=total, nnz=nnz, vocab=V)
     master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
@@ -527,6 +532,45 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
 
 def as_device_matches(m):
     return m if isinstance(m, DeviceMatches) else matches_from_scipy(m)
+
+
+def empty_csr(like, n_rows):
+    """A CSR block with `n_rows` empty rows on the device of `like` (ranks that own no rows of a sharded matrix)."""
+    t = torch()
+    dev = like.device
+    val = _empty(1, t.float32 if like.dtype == np.float32 else t.float64, dev)
+    val32 = val if like.dtype == np.float32 else _empty(1, t.float32, dev)
+    return DeviceCSR((n_rows, like.shape[1]), t.zeros(n_rows + 1, dtype=t.int64, device=dev),
+                     _empty(1, t.int32, dev), val, val32, 0, like.dtype, like.norm_bound)
+
+
+def offset_rows(m, row_offset, n_rows_total):
+    """Row ids of a per-rank block -> ids in the full left matrix."""
+    if m.nnz:
+        m.d_row[:m.nnz] += int(row_offset)
+    return DeviceMatches((int(n_rows_total), m.shape[1]), m.d_row, m.d_col, m.d_score, m.nnz, m.max_row,
+                         out_dtype=m.out_dtype)
+
+
+def allgather_csr(M, n_rows_total):
+    """Right matrix sharded by rows over the ranks (sharded K1) -> the full matrix on every rank (NCCL all-gather
+    over NVLink of row lengths, indices and values)."""
+    from . import _dist
+    t = torch()
+    n = M.shape[0]
+    lo, hi = M.base, M.base + M.nnz
+    row_len = (M.d_indptr[1:n + 1] - M.d_indptr[:n]).contiguous()
+    vals = (M.d_val[lo:hi].contiguous(),) if M.d_val is M.d_val32 else (M.d_val[lo:hi].contiguous(),
+                                                                         M.d_val32[lo:hi].contiguous())
+    indptr, indices, gvals = _dist.allgather_csr_rows(row_len, M.d_indices[lo:hi].contiguous(), vals)
+    nnz = int(indptr[-1].item())
+    if nnz == 0:
+        indices = _empty(1, t.int32, M.device)
+        gvals = tuple(_empty(1, v.dtype, M.device) for v in vals)
+    val = gvals[0]
+    val32 = gvals[0] if len(gvals) == 1 else gvals[1]
+    out = DeviceCSR((int(n_rows_total), M.shape[1]), indptr, indices, val, val32, nnz, M.dtype, M.norm_bound)
+    return out
 
 
 def gather_shards(m):

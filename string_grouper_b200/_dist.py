@@ -71,5 +71,39 @@ def gather_matches(shape, row, col, score, nnz, max_row):
     return g_row, g_col, g_score, int(sum(lens)), int(mx.item())
 
 
+def shard_vectorise(n_bytes_total):
+    """Whether K1 should be sharded over the ranks (two-Series inputs only).  SG_B200_SHARD_VECTORISE = 0 / 1 /
+    auto (default): auto shards once the packed corpus exceeds 256 MB — below that every rank vectorising
+    everything costs a few milliseconds and needs no collective at all."""
+    import os
+    mode = os.environ.get("SG_B200_SHARD_VECTORISE", "auto").lower()
+    if mode in ("1", "true", "yes", "on"):
+        return True
+    if mode in ("0", "false", "no", "off"):
+        return False
+    return n_bytes_total > (256 << 20)
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over the ranks (the int32 document-frequency table of K1: ncclAllReduce over NVLink)."""
+    dist = _dist()
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def allgather_csr_rows(row_len, indices, vals):
+    """All-gather a row-sharded CSR (the right matrix after a sharded K1).
+
+    row_len: int64 lengths of the local rows; indices: int32 [local nnz]; vals: tuple of value tensors
+    [local nnz].  Returns (indptr int64 [n_total+1], indices, vals) of the concatenation in rank order.
+    """
+    import torch
+    (all_len,), _ = allgather_varlen((row_len,))
+    gathered, _ = allgather_varlen((indices,) + tuple(vals))
+    indptr = torch.zeros(all_len.numel() + 1, dtype=torch.int64, device=row_len.device)
+    torch.cumsum(all_len, 0, out=indptr[1:])
+    return indptr, gathered[0], gathered[1:]
+
+
 def shard_offsets(n_rows, world_size):
     return np.array([shard_range(n_rows, r, world_size)[0] for r in range(world_size)] + [n_rows], dtype=np.int64)

@@ -171,13 +171,14 @@ struct IdfMath<float> {
 // idf = log(n/df)+1 in T; x = tf*idf in T; sum of squares in double in column order; x / sqrt(sum).
 template <typename T>
 __global__ void __launch_bounds__(K1_WARPS * 32)
-tfidf_finalize_kernel(const int64_t *__restrict__ offsets, int64_t n_docs, const int32_t *__restrict__ df,
+tfidf_finalize_kernel(const int64_t *__restrict__ offsets, int64_t n_docs, int64_t n_docs_fit,
+                      const int32_t *__restrict__ df,
                       const int32_t *__restrict__ rank, const uint32_t *__restrict__ scratch_key,
                       const uint32_t *__restrict__ scratch_tf, const int32_t *__restrict__ row_nnz,
                       const int64_t *__restrict__ indptr, int32_t *__restrict__ indices,
                       double *__restrict__ val64, float *__restrict__ val32) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n1 = n_docs + 1;
+    const int64_t n1 = n_docs_fit + 1;   // smooth_idf: one extra document (sklearn TfidfTransformer.fit)
     for (int64_t doc = (int64_t)blockIdx.x * K1_WARPS + warp; doc < n_docs; doc += (int64_t)gridDim.x * K1_WARPS) {
         const int nnz = row_nnz[doc];
         if (nnz == 0) continue;
@@ -251,7 +252,8 @@ size_t sg_tfidf_finalize_workspace_bytes(int64_t n_docs, int ngram) {
     return align_up((size_t)slots * 4, 256) + align_up(b1 > b2 ? b1 : b2, 256) + 1024;
 }
 
-int sg_tfidf_finalize(const int64_t *offsets, int64_t n_docs, int ngram, int dtype, const int32_t *df_table,
+int sg_tfidf_finalize(const int64_t *offsets, int64_t n_docs, int64_t n_docs_fit, int ngram, int dtype,
+                      const int32_t *df_table,
                       int32_t *rank_table, const uint32_t *scratch_key, const uint32_t *scratch_tf,
                       int32_t *row_nnz, int64_t *indptr, int32_t *indices, double *val64, float *val32,
                       int32_t *vocab_size, int64_t *nnz_total, void *ws, size_t ws_bytes, void *stream_) {
@@ -260,7 +262,7 @@ int sg_tfidf_finalize(const int64_t *offsets, int64_t n_docs, int ngram, int dty
     if (slots < 0) return fail(SG_ERR_UNSUPPORTED, "ngram_size %d unsupported (1..4)", ngram);
     if (dtype != SG_DTYPE_F32 && dtype != SG_DTYPE_F64) return fail(SG_ERR_INVALID, "bad dtype");
     if (dtype == SG_DTYPE_F64 && !val64) return fail(SG_ERR_INVALID, "val64 is required for float64");
-    if (n_docs < 0) return fail(SG_ERR_INVALID, "negative n_docs");
+    if (n_docs < 0 || n_docs_fit < n_docs) return fail(SG_ERR_INVALID, "need 0 <= n_docs <= n_docs_fit");
     Arena ar(ws, ws_bytes);
     int32_t *flag = ar.take<int32_t>((size_t)slots);
     size_t b1 = 0, b2 = 0;
@@ -289,12 +291,12 @@ int sg_tfidf_finalize(const int64_t *offsets, int64_t n_docs, int ngram, int dty
         if (grid > cap) grid = cap;
         if (dtype == SG_DTYPE_F64)
             tfidf_finalize_kernel<double><<<(unsigned)grid, K1_WARPS * 32, 0, st>>>(
-                offsets, n_docs, df_table, rank_table, scratch_key, scratch_tf, row_nnz, indptr, indices, val64,
-                val32);
+                offsets, n_docs, n_docs_fit, df_table, rank_table, scratch_key, scratch_tf, row_nnz, indptr, indices,
+                val64, val32);
         else
             tfidf_finalize_kernel<float><<<(unsigned)grid, K1_WARPS * 32, 0, st>>>(
-                offsets, n_docs, df_table, rank_table, scratch_key, scratch_tf, row_nnz, indptr, indices, nullptr,
-                val32);
+                offsets, n_docs, n_docs_fit, df_table, rank_table, scratch_key, scratch_tf, row_nnz, indptr, indices,
+                nullptr, val32);
         SG_LAUNCH_CHECK();
     }
     return SG_OK;

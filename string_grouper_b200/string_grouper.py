@@ -252,11 +252,11 @@ class StringGrouper(object):
         """Row-wise similarity of master and duplicates (ref:433-440)."""
         if len(self._master) != len(self._duplicates):
             raise Exception("To perform this function, both input Series must have the same length.")
-        master_matrix, duplicate_matrix = self._get_tf_idf_matrices()
+        master_matrix, duplicate_matrix = self._get_tf_idf_matrices(shard=False)
         sims = _device.rowwise_dot(_device.as_device_csr(master_matrix), _device.as_device_csr(duplicate_matrix))
         return pd.Series(sims, name='similarity', index=self._master.index)
 
-    def _get_tf_idf_matrices(self):
+    def _get_tf_idf_matrices(self, shard=True):
         """(master_matrix, duplicate_matrix) as HBM-resident CSR (ref:685-697).
 
         The vocabulary / idf are fitted on master ++ duplicates (ref:699-707); with no duplicates the second
@@ -265,10 +265,31 @@ class StringGrouper(object):
         """
         cfg = self._config
         series = [self._master] if self._duplicates is None else [self._master, self._duplicates]
-        data, offsets, flags = _ingest.pack_strings(series, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+        rank, world_size = _dist.world()
+        approx_bytes = (sum(int(s.str.len().sum()) for s in series)
+                        if shard and world_size > 1 and len(series) == 2 else 0)
         stats = {}
-        master, dup, vocab = _device.tfidf(data, offsets, len(self._master), cfg.ngram_size, flags,
-                                           cfg.tfidf_matrix_dtype, stats=stats)
+        if shard and world_size > 1 and len(series) == 2 and _dist.shard_vectorise(approx_bytes):
+            # two Series over several GPUs: every rank vectorises only its blocks of master and duplicates rows;
+            # document frequencies are all-reduced (NCCL), the duplicate matrix is all-gathered over NVLink,
+            # the master block stays local and is this rank's share of the left rows of _build_matches.
+            n_m, n_d = len(self._master), len(self._duplicates)
+            mlo, mhi = _dist.shard_range(n_m, rank, world_size)
+            dlo, dhi = _dist.shard_range(n_d, rank, world_size)
+            local = [self._master.iloc[mlo:mhi], self._duplicates.iloc[dlo:dhi]]
+            data, offsets, flags = _ingest.pack_strings(local, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+            master, dup, vocab = _device.tfidf(data, offsets, mhi - mlo, cfg.ngram_size, flags,
+                                               cfg.tfidf_matrix_dtype, stats=stats,
+                                               df_allreduce=_dist.allreduce_sum_, n_docs_fit=n_m + n_d)
+            if dup is None:      # this rank holds no duplicate rows: an empty block still takes part in the gather
+                dup = _device.empty_csr(master, 0)
+            dup = _device.allgather_csr(dup, n_d)
+            master.row_offset, master.global_rows = mlo, n_m
+            stats["sharded_vectorise"] = True
+        else:
+            data, offsets, flags = _ingest.pack_strings(series, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+            master, dup, vocab = _device.tfidf(data, offsets, len(self._master), cfg.ngram_size, flags,
+                                               cfg.tfidf_matrix_dtype, stats=stats)
         self._vocabulary = vocab
         self._last_stats = stats
         return master, (master if dup is None else dup)
@@ -283,7 +304,13 @@ class StringGrouper(object):
         A = _device.as_device_csr(master_matrix)
         B = A if duplicate_matrix is master_matrix else _device.as_device_csr(duplicate_matrix)
         rank, world_size = _dist.world()
-        if world_size > 1:
+        if world_size > 1 and getattr(A, "row_offset", None) is not None:
+            # K1 was sharded: A already IS this rank's block of left rows
+            out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity,
+                                      stats=self._last_stats)
+            out = _device.offset_rows(out, A.row_offset, A.global_rows)
+            out = _device.gather_shards(out)
+        elif world_size > 1:
             # one process per GPU: this rank computes its block of left rows, the blocks are all-gathered
             lo, hi = _dist.shard_range(A.shape[0], rank, world_size)
             out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity, row_begin=lo,

@@ -20,6 +20,15 @@ dupes = pd.Series(make_names(7000, seed=92) + make_names(30011, seed=91)[:999])
 a = api.match_strings(names, min_similarity=0.8)
 b = api.match_strings(names, dupes, min_similarity=0.7, max_n_matches=5)
 g = api.group_similar_strings(names)
+os.environ["SG_B200_SHARD_VECTORISE"] = "1"      # sharded K1: df all-reduce + all-gather of the duplicate matrix
+sg = api.StringGrouper(names, dupes, min_similarity=0.7, max_n_matches=5).fit()
+assert sg._last_stats.get("sharded_vectorise")
+b2 = sg.get_matches()
+m2 = api.match_most_similar(names, dupes, min_similarity=0.7)
+os.environ["SG_B200_SHARD_VECTORISE"] = "0"
+m1 = api.match_most_similar(names, dupes, min_similarity=0.7)
+pd.testing.assert_frame_equal(b, b2)
+pd.testing.assert_frame_equal(m1, m2) if isinstance(m1, pd.DataFrame) else pd.testing.assert_series_equal(m1, m2)
 a.to_pickle("%s.self.%d.pkl" % (out, rank))
 b.to_pickle("%s.two.%d.pkl" % (out, rank))
 g.to_pickle("%s.grp.%d.pkl" % (out, rank))
