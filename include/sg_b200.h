@@ -222,6 +222,17 @@ int sg_symmetrize(int64_t n, int64_t nnz_in, int flags, const int32_t *in_row, c
                   const double *in_score, int32_t *out_row, int32_t *out_col, double *out_score,
                   int64_t *out_nnz /*[dev] 1*/, void *ws, size_t ws_bytes, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Group representatives.  Replaces the arithmetic of StringGrouper._deduplicate
+ * (sg.py:851-904): weakly connected components of the match graph (:863), per-row similarity sums
+ * (:875-881), representative = first member (group_rep='first') or first member with the largest sum
+ * ('centroid', idxmax :885-886).  Input: the match list sorted by (row, col) as K4 leaves it.
+ * This call synchronises the stream once per component-sweep round (a handful).
+ * ------------------------------------------------------------------------- */
+size_t sg_group_reps_workspace_bytes(int64_t n);
+int sg_group_reps(int64_t n, int64_t nnz, const int32_t *row, const int32_t *col, const double *score,
+                  int centroid, int32_t *rep /*[dev] n*/, void *ws, size_t ws_bytes, void *stream);
+
 /* row-wise dot of two CSR matrices of equal shape (StringGrouper.dot, sg.py:433-440) */
 int sg_rowwise_dot(int64_t n_rows, const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
                    const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,

@@ -14,7 +14,7 @@ _TORCH = None
 
 # hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
-                 "rowdot": 0, "order": 0, "tiles": 0}
+                 "rowdot": 0, "order": 0, "tiles": 0, "groups": 0}
 
 DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "768"))
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
@@ -400,6 +400,21 @@ def symmetrize(M, fix_diagonal=True, mirror=True):
     LAUNCH_COUNTS["symmetrize"] += 3
     nnz = int(out_nnz.item())
     return DeviceMatches(M.shape, out_row, out_col, out_score, nnz, M.max_row, out_dtype=M.out_dtype)
+
+
+def group_reps(M, n, centroid):
+    """Representative index of every string's group from the (row, col)-sorted device match list
+    (StringGrouper._deduplicate, string_grouper.py:851-904)."""
+    t = require_cuda()
+    L = _lib.load()
+    dev = M.d_row.device
+    rep = _empty(n, t.int32, dev)
+    ws_bytes = int(L.sg_group_reps_workspace_bytes(n))
+    ws = _empty(ws_bytes, t.uint8, dev)
+    _lib.check(L.sg_group_reps(n, M.nnz, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), 1 if centroid else 0,
+                               _ptr(rep), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["groups"] += 6
+    return rep[:n].cpu().numpy().astype(np.int64)
 
 
 def matches_from_scipy(m):

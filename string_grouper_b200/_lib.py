@@ -58,6 +58,8 @@ SIGNATURES = {
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_symmetrize_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_symmetrize": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_group_reps_workspace_bytes": (_sz, [_i64]),
+    "sg_group_reps": (_i32, [_i64, _i64, _p, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_rowwise_dot": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
 }
 

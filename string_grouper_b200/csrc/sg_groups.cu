@@ -1,0 +1,131 @@
+// Group representatives on the device, for sm_100a  (SURVEY.md §8f row 2).
+//
+// Replaces the arithmetic of StringGrouper._deduplicate
+// (/root/reference/string_grouper/string_grouper.py:851-904): weakly connected components of the match
+// graph (scipy.sparse.csgraph.connected_components, :863), per-row similarity sums (:875-881) and the
+// per-group choice of the representative: the first member ('first', :872-873) or the first member with
+// the largest similarity sum ('centroid', :885-886, idxmax).
+//
+// Components: min-label hooking with atomicMin + pointer jumping until nothing changes; the label of a
+// component ends up being its smallest member index, which is also the 'first' representative.
+// Row sums are accumulated sequentially in storage order (the list is sorted by row, then column, exactly
+// the order in which scipy's CSR row sum adds them), so 'centroid' ties resolve as in the reference.
+#include "sg_common.cuh"
+
+namespace sg {
+
+__global__ void cc_init_kernel(int64_t n, int32_t *__restrict__ label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) label[i] = (int32_t)i;
+}
+
+__global__ void cc_hook_kernel(int64_t nnz, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                               int32_t *__restrict__ label, int32_t *__restrict__ changed) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int32_t lu = label[row[e]], lv = label[col[e]];
+    if (lu == lv) return;
+    const int32_t hi = lu > lv ? lu : lv, lo = lu > lv ? lv : lu;
+    atomicMin(label + hi, lo);
+    *changed = 1;
+}
+
+__global__ void cc_compress_kernel(int64_t n, int32_t *__restrict__ label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t l = label[i];
+    while (label[l] != l) l = label[l];
+    label[i] = l;
+}
+
+__device__ __forceinline__ uint64_t orderable(double x) {
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// one thread per row: [lower_bound(row, i), lower_bound(row, i+1)) summed in storage order
+__global__ void cc_rowsum_kernel(int64_t n, int64_t nnz, const int32_t *__restrict__ row,
+                                 const double *__restrict__ score, const int32_t *__restrict__ label,
+                                 double *__restrict__ weight, unsigned long long *__restrict__ best) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (row[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    double s = 0.0;
+    for (int64_t p = lo; p < nnz && row[p] == i; ++p) s = __dadd_rn(s, score[p]);
+    weight[i] = s;
+    atomicMax(best + label[i], (unsigned long long)orderable(s));
+}
+
+__global__ void cc_pick_kernel(int64_t n, const int32_t *__restrict__ label, const double *__restrict__ weight,
+                               const unsigned long long *__restrict__ best, int32_t *__restrict__ rep_of_root) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = label[i];
+    if ((unsigned long long)orderable(weight[i]) == best[r]) atomicMin(rep_of_root + r, (int32_t)i);
+}
+
+__global__ void cc_assign_kernel(int64_t n, const int32_t *__restrict__ label, const int32_t *__restrict__ rep_of_root,
+                                 int32_t *__restrict__ rep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rep[i] = rep_of_root ? rep_of_root[label[i]] : label[i];
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+size_t sg_group_reps_workspace_bytes(int64_t n) {
+    return 2 * align_up((size_t)(n + 1) * 4, 256) + 2 * align_up((size_t)(n + 1) * 8, 256) + 1024;
+}
+
+// Matches (row, col, score) sorted by (row, col) over n strings -> rep[i] = index of the representative of
+// i's group.  centroid = 0: first member; 1: first member with the largest similarity sum.
+// The component sweep reads one int32 back per round (a handful of rounds).
+int sg_group_reps(int64_t n, int64_t nnz, const int32_t *row, const int32_t *col, const double *score, int centroid,
+                  int32_t *rep, void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n <= 0) return SG_OK;
+    Arena ar(ws, ws_bytes);
+    int32_t *label = ar.take<int32_t>((size_t)n + 1);      // label[n] doubles as the "changed" flag
+    int32_t *rep_of_root = ar.take<int32_t>((size_t)n + 1);
+    double *weight = ar.take<double>((size_t)n + 1);
+    unsigned long long *best = ar.take<unsigned long long>((size_t)n + 1);
+    if (!ar.ok()) return fail(SG_ERR_INVALID, "group workspace too small (%zu < %zu)", ws_bytes, ar.off);
+    int32_t *changed = label + n;
+    const unsigned gn = (unsigned)((n + 255) / 256);
+    const unsigned ge = (unsigned)((nnz + 255) / 256);
+    cc_init_kernel<<<gn, 256, 0, st>>>(n, label);
+    SG_LAUNCH_CHECK();
+    for (int round = 0; nnz > 0 && round < 10000; ++round) {
+        SG_CUDA_TRY(cudaMemsetAsync(changed, 0, sizeof(int32_t), st));
+        cc_hook_kernel<<<ge, 256, 0, st>>>(nnz, row, col, label, changed);
+        SG_LAUNCH_CHECK();
+        cc_compress_kernel<<<gn, 256, 0, st>>>(n, label);
+        SG_LAUNCH_CHECK();
+        int32_t h = 0;
+        SG_CUDA_TRY(cudaMemcpyAsync(&h, changed, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!h) break;
+    }
+    if (centroid) {
+        SG_CUDA_TRY(cudaMemsetAsync(best, 0, (size_t)n * 8, st));
+        SG_CUDA_TRY(cudaMemsetAsync(rep_of_root, 0x7f, (size_t)n * 4, st));
+        cc_rowsum_kernel<<<gn, 256, 0, st>>>(n, nnz, row, score, label, weight, best);
+        SG_LAUNCH_CHECK();
+        cc_pick_kernel<<<gn, 256, 0, st>>>(n, label, weight, best, rep_of_root);
+        SG_LAUNCH_CHECK();
+        cc_assign_kernel<<<gn, 256, 0, st>>>(n, label, rep_of_root, rep);
+    } else {
+        cc_assign_kernel<<<gn, 256, 0, st>>>(n, label, nullptr, rep);
+    }
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+}  // extern "C"

@@ -137,6 +137,7 @@ class StringGrouper(object):
         self._config = StringGrouperConfig(**kwargs)
         self._n_blocks = self._config.n_blocks
         self._vocabulary = None          # device df / rank tables of the last fit (K1)
+        self._matches_device = None      # match list in HBM as long as it equals _matches_list
         self._last_stats = {}
         self._set_data(master, duplicates, master_id, duplicates_id)
         self._set_options(**kwargs)
@@ -245,6 +246,7 @@ class StringGrouper(object):
             matches = _device.apply_pending(matches)
 
         self._matches_list = self._get_matches_list(matches)
+        self._matches_device = matches if hasattr(matches, "d_row") else None   # HBM copy for get_groups()
         self.is_build = True
         return self
 
@@ -336,7 +338,7 @@ class StringGrouper(object):
             s = m.data
         return pd.DataFrame({'master_side': np.asarray(r).astype(np.int64),
                              'dupe_side': np.asarray(c).astype(np.int64),
-                             'similarity': np.asarray(s)})
+                             'similarity': np.asarray(s)}, copy=False)
 
     @staticmethod
     def _fix_diagonal(m):
@@ -426,6 +428,7 @@ class StringGrouper(object):
             new = pd.concat([new, new.rename(columns={'master_side': 'dupe_side', 'dupe_side': 'master_side'})[
                 ['master_side', 'dupe_side', 'similarity']]])
         self._matches_list = pd.concat([self._matches_list.drop_duplicates(), new], ignore_index=True)
+        self._matches_device = None
         return self
 
     @validate_is_fit
@@ -436,6 +439,7 @@ class StringGrouper(object):
             dupe_idx = master_idx
         hit = self._matches_list.master_side.isin(master_idx) & self._matches_list.dupe_side.isin(dupe_idx)
         self._matches_list = self._matches_list[~hit]
+        self._matches_device = None
         return self
 
     # ------------------------------------------------------------------ result shaping helpers
@@ -503,22 +507,28 @@ class StringGrouper(object):
 
     def _deduplicate(self, ignore_index=False) -> Union[pd.DataFrame, pd.Series]:
         """Connected components of the match graph, one representative per group (ref:851-904)."""
-        pairs = self._matches_list
         n = len(self._master)
-        rows, cols = pairs.master_side.to_numpy(), pairs.dupe_side.to_numpy()
-        graph = csr_matrix((np.full(len(pairs), 1), (rows, cols)), shape=(n, n))
-        _, group = connected_components(csgraph=graph, directed=True)
-        if self._config.group_rep == GROUP_REP_CENTROID:
-            graph.data = pairs['similarity'].to_numpy()
-            weight = np.asarray(graph.sum(axis=1)).squeeze(axis=1)
-            order = np.lexsort((np.arange(n), -weight, group))   # per group: weight desc, first index on ties
+        centroid = self._config.group_rep == GROUP_REP_CENTROID
+        if self._matches_device is not None:
+            # components, similarity sums and representatives on the device (csrc/sg_groups.cu)
+            rep = _device.group_reps(self._matches_device, n, centroid)
         else:
-            order = np.lexsort((np.arange(n), group))            # per group: first index
-        head = np.ones(n, dtype=bool)
-        head[1:] = group[order][1:] != group[order][:-1]
-        rep_of_group = np.empty(group.max() + 1 if n else 0, dtype=np.int64)
-        rep_of_group[group[order][head]] = order[head]
-        rep = rep_of_group[group]
+            # the list was edited by add_match / remove_match: host statement of the same rule
+            pairs = self._matches_list
+            rows, cols = pairs.master_side.to_numpy(), pairs.dupe_side.to_numpy()
+            graph = csr_matrix((np.full(len(pairs), 1), (rows, cols)), shape=(n, n))
+            _, group = connected_components(csgraph=graph, directed=True)
+            if centroid:
+                graph.data = pairs['similarity'].to_numpy()
+                weight = np.asarray(graph.sum(axis=1)).squeeze(axis=1)
+                order = np.lexsort((np.arange(n), -weight, group))   # per group: weight desc, first index on ties
+            else:
+                order = np.lexsort((np.arange(n), group))            # per group: first index
+            head = np.ones(n, dtype=bool)
+            head[1:] = group[order][1:] != group[order][:-1]
+            rep_of_group = np.empty(group.max() + 1 if n else 0, dtype=np.int64)
+            rep_of_group[group[order][head]] = order[head]
+            rep = rep_of_group[group]
 
         prefix = GROUP_REP_PREFIX
         label = f'{prefix}{self._master.name}' if self._master.name else prefix[:-1]
@@ -591,10 +601,21 @@ class StringGrouper(object):
 def _take_side(series, positions, default_name, drop_index, prefix, mirror):
     """Rows of `series` at `positions` as prefixed column(s); index levels become columns unless dropped.
     `mirror` puts the value column first (right-hand side of get_matches, ref:468)."""
+    name = series.name if series.name else default_name
+    index = series.index
+    if drop_index or (index.nlevels == 1 and index.name is None and name != 'index'):
+        # fast path (millions of matches): one take on the backing array, one on the index values
+        values = pd.Series(series.array.take(positions), name=f"{prefix}{name}", copy=False)
+        if drop_index:
+            return values
+        if isinstance(index, pd.RangeIndex):
+            labels = index.start + index.step * np.asarray(positions, dtype=np.int64)
+        else:
+            labels = index.to_numpy()[positions]
+        level = pd.Series(labels, name=f"{prefix}index", copy=False)
+        return pd.concat([values, level] if mirror else [level, values], axis=1)
     named = series if series.name else series.rename(default_name)
-    taken = named.iloc[positions].reset_index(drop=drop_index)
-    if isinstance(taken, pd.Series):
-        return taken.rename(f"{prefix}{taken.name}")
+    taken = named.iloc[positions].reset_index(drop=False)
     if mirror:
         taken = taken[taken.columns[::-1]]
     return taken.rename(columns={c: f"{prefix}{c}" for c in taken.columns})

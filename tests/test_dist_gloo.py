@@ -38,6 +38,20 @@ WORKER = textwrap.dedent('''
         g = api.group_similar_strings(names, min_similarity=0.7)
     a.to_pickle("%(out)s.self.%%s.pkl" %% sys.argv[1]); b.to_pickle("%(out)s.two.%%s.pkl" %% sys.argv[1])
     g.to_pickle("%(out)s.grp.%%s.pkl" %% sys.argv[1])
+    # row-sharded CSR all-gather and df all-reduce used by the sharded vectoriser
+    import torch, scipy.sparse as sp
+    from string_grouper_b200 import _dist
+    rank = int(sys.argv[1])
+    full = sp.random(37, 11, density=0.3, format="csr", random_state=5, dtype=np.float64)
+    lo, hi = _dist.shard_range(37, rank, 2)
+    part = full[lo:hi]
+    indptr, idx, (val,) = _dist.allgather_csr_rows(torch.from_numpy(np.diff(part.indptr).astype(np.int64)),
+                                                   torch.from_numpy(part.indices.astype(np.int32)),
+                                                   (torch.from_numpy(part.data.copy()),))
+    assert np.array_equal(indptr.numpy(), full.indptr) and np.array_equal(idx.numpy(), full.indices)
+    assert np.array_equal(val.numpy(), full.data)
+    df = torch.full((8,), rank + 1, dtype=torch.int32)
+    assert _dist.allreduce_sum_(df).tolist() == [3] * 8
     dist.destroy_process_group()
 ''')
 

@@ -100,3 +100,18 @@ def test_match_strings_two_series_frame_equals_oracle():
     b = set(zip(ref.master_side.tolist(), ref.dupe_side.tolist()))
     assert len(a ^ b) <= 0.01 * len(b)         # top-3 ties between identical strings may differ
     assert (out.left_company.to_numpy() == master.to_numpy()[out.left_index.to_numpy()]).all()
+
+
+@pytest.mark.parametrize("group_rep", ["centroid", "first"])
+def test_group_representatives_equal_host_rule(group_rep):
+    """device connected components / centroid choice (csrc/sg_groups.cu) vs the scipy statement of
+    StringGrouper._deduplicate (reference string_grouper.py:851-904) on the same match list."""
+    from string_grouper_b200 import StringGrouper
+    names = pd.Series(make_names(30000, seed=61), name="name")
+    sg = StringGrouper(names, min_similarity=0.8, group_rep=group_rep).fit()
+    assert sg._matches_device is not None
+    dev = sg.get_groups()
+    sg._matches_device = None          # same object, host rule
+    host = sg.get_groups()
+    pd.testing.assert_frame_equal(dev, host)
+    assert (dev["group_rep_index"] != np.arange(len(names))).sum() > 1000
