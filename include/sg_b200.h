@@ -113,8 +113,9 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w);
  * `Bi.T`, sg.py:727/:738, done once and laid out for the kernel).  The right rows are taken in the
  * order `rank` (position of every row in heavy-feature signature order, sg_row_order; NULL = input
  * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (t, f) = the docs of feature f
- * inside tile t, sorted by position, at bucket_ptr[t*(n_cols+1)+f]; a posting is 8 bytes
- * {int32 position - t*tile_w, float w}.  `bucket_dir` (optional) receives the same directory as aligned
+ * inside tile t, sorted by position, at bucket_ptr[t*(n_cols+1)+f]; a posting is 4 bytes:
+ * position - t*tile_w in the low 16 bits, the weight rounded to fp16 in the high 16 bits (candidate
+ * scores only need to be within the caller's margin; every candidate is re-scored exactly).  `bucket_dir` (optional) receives the same directory as aligned
  * {int32 start, int32 length} pairs, T*(n_cols+1) of them, the form sg_cossim_candidates reads.
  * `indptr` may be a row-range view (indptr_base = indptr[0]).
  */
@@ -122,8 +123,9 @@ size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles)
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr /*[dev]*/,
                       const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
                       const int32_t *rank /*[dev] or NULL*/, int tile_w, int64_t indptr_base,
+                      float w_scale /* weights are multiplied by this before the fp16 rounding: 1 / max|w| */,
                       int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/,
-                      void *bucket_dir /*[dev] T*(n_cols+1)*8 B or NULL*/, void *postings /*[dev] nnz*8 B*/,
+                      void *bucket_dir /*[dev] T*(n_cols+1)*8 B or NULL*/, void *postings /*[dev] nnz*4 B*/,
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
 /*
@@ -144,6 +146,7 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_ind
                          int64_t n_right, int64_t n_cols, const void *bucket_dir /*[dev] {start,len} pairs*/,
                          const void *postings /*[dev]*/,
                          const int32_t *perm_b /*[dev] position -> right row id, or NULL*/, int tile_w,
+                         float a_scale /* left weights are multiplied by this: the inverse of w_scale */,
                          float cand_threshold,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
                          int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
@@ -179,10 +182,10 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
                    void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
- * K2, formulation 2 (csrc/sg_order.cu, csrc/sg_cossim2.cu): same contract as sg_cossim_candidates —
- * it feeds sg_rescore / sg_topn_select — but both operands are taken in heavy-feature signature order
- * and a warp owns a tile of `rows_per_tile` left rows x `tile_w` columns, so one posting read serves
- * every row of the tile and the lanes of a step hit distinct shared-memory banks.
+ * Row ordering for K2 (csrc/sg_order.cu): both operands of C = A*B^T are processed in heavy-feature
+ * signature order, so that the docs of a frequent n-gram are runs of consecutive column positions (the
+ * lanes of a posting step hit distinct shared-memory banks) and neighbouring warps stream the same buckets.
+ * No reference counterpart (the reference's block loop takes rows in input order, sg.py:734-750).
  * ------------------------------------------------------------------------- */
 size_t sg_order_workspace_bytes(int64_t n_rows, int64_t n_cols);
 /* hrank[n_cols] int8: rank among the n_heavy (<= 64) most frequent features of the matrix, else -1 */
@@ -192,21 +195,6 @@ int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, con
 int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
                  const int8_t *hrank, int32_t *perm /*[dev]*/, int32_t *rank /*[dev] or NULL*/, void *ws,
                  size_t ws_bytes, void *stream);
-/* left rows perm[0..n_rows) -> per-tile lists sorted by feature.  row_pos[n_rows+1]; tl_ra[nnz] {row, w};
- * seg_f / seg_start [nnz + n_tiles + 1] (tile t at row_pos[t*R] + t); tile_nseg[n_tiles]. */
-size_t sg_left_tiles_workspace_bytes(int64_t n_rows, int64_t nnz);
-int sg_left_tiles_build(int64_t n_rows, int64_t nnz, int rows_per_tile, const int64_t *indptr,
-                        const int32_t *indices, const float *val32, const int32_t *perm, int64_t *row_pos,
-                        void *tl_ra, int32_t *seg_f, int32_t *seg_start, int32_t *tile_nseg, void *ws,
-                        size_t ws_bytes, void *stream);
-size_t sg_cossim2_smem_bytes(int warps_per_cta, int rows_per_tile, int tile_w);
-int sg_cossim2_candidates(const int64_t *row_pos, const void *tl_ra, const int32_t *seg_f, const int32_t *seg_start,
-                          const int32_t *tile_nseg, int64_t n_left_rows, const int32_t *perm_a,
-                          const int32_t *bucket_ptr, const void *postings, int64_t n_cols, int tile_w,
-                          int64_t tiles_per_group, int64_t n_right, const int32_t *perm_b, float cand_threshold,
-                          int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
-                          unsigned long long *cand_count /*[dev] 1*/, unsigned long long *queue /*[dev] 1*/,
-                          int warps_per_cta, int rows_per_tile, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * K4 — self-match post-processing.

@@ -19,11 +19,7 @@ LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "sym
 DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "768"))
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
-K2_ALGO = int(os.environ.get("SG_B200_K2", "1"))            # 1 = row-wise (default), 2 = experimental tiled formulation
-V2_TILE_W = int(os.environ.get("SG_B200_V2_TILE_W", "320"))
-V2_WARPS = int(os.environ.get("SG_B200_V2_WARPS", "16"))
-V2_ROWS = int(os.environ.get("SG_B200_V2_ROWS", "8"))
-CAND_MARGIN = 2.0e-4   # fp32 candidate scores are re-scored exactly; see DESIGN.md §K2
+CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
 
 
 def torch():
@@ -180,34 +176,16 @@ def right_side(B, tile_w):
             raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
         bucket_ptr = _empty(nb, t.int32, B.device)
         bucket_dir = _empty(2 * nb, t.int32, B.device)
-        post = _empty(2 * max(B.nnz, 1), t.int32, B.device)
+        post = _empty(max(B.nnz, 1), t.int32, B.device)
         ws_bytes = int(L.sg_postings_workspace_bytes(B.nnz, n_cols, T))
         ws = _empty(ws_bytes, t.uint8, B.device)
         _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
-                                       _ptr(rank), tile_w, B.base, _ptr(bucket_ptr), _ptr(bucket_dir), _ptr(post),
+                                       _ptr(rank), tile_w, B.base, 1.0 / max(B.norm_bound, 1.0), _ptr(bucket_ptr),
+                                       _ptr(bucket_dir), _ptr(post),
                                        _ptr(ws), ws_bytes, _stream()))
         LAUNCH_COUNTS["postings"] += 3
         B._postings2[tile_w] = (bucket_ptr, bucket_dir, post, T)
     return (hrank, perm, rank) + B._postings2[tile_w]
-
-
-def left_tiles_v2(A, perm, n_rows, rows_per_tile):
-    t = require_cuda()
-    L = _lib.load()
-    n_tiles = (n_rows + rows_per_tile - 1) // rows_per_tile
-    nnz_cap = A.nnz if (n_rows == A.shape[0]) else A.nnz_parent
-    row_pos = _empty(n_rows + 1, t.int64, A.device)
-    tl_ra = _empty(2 * max(nnz_cap, 1), t.int32, A.device)
-    seg_f = _empty(nnz_cap + n_tiles + 1, t.int32, A.device)
-    seg_start = _empty(nnz_cap + n_tiles + 1, t.int32, A.device)
-    tile_nseg = _empty(n_tiles, t.int32, A.device)
-    ws_bytes = int(L.sg_left_tiles_workspace_bytes(n_rows, nnz_cap))
-    ws = _empty(ws_bytes, t.uint8, A.device)
-    _lib.check(L.sg_left_tiles_build(n_rows, nnz_cap, rows_per_tile, _ptr(A.d_indptr), _ptr(A.d_indices),
-                                     _ptr(A.d_val32), _ptr(perm), _ptr(row_pos), _ptr(tl_ra), _ptr(seg_f),
-                                     _ptr(seg_start), _ptr(tile_nseg), _ptr(ws), ws_bytes, _stream()))
-    LAUNCH_COUNTS["tiles"] += 2
-    return row_pos, tl_ra, seg_f, seg_start, tile_nseg
 
 
 class DeviceMatches:
@@ -266,8 +244,7 @@ def pick_tile(n_right, tile_w=None, warps=None):
     return min(tile_w, need), warps
 
 
-def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None, algo=None,
-                rows_per_tile=None):
+def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None):
     """C[i,:] = top_n{ j : A_i . B_j > threshold } for rows [row_begin,row_end) of A.
 
     Device counterpart of the whole block loop of StringGrouper._build_matches
@@ -291,23 +268,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         z32 = _empty(1, t.int32, dev)
         return DeviceMatches(shape, z32, z32, _empty(1, t.float64, dev), 0, 0)
 
-    algo = int(algo or K2_ALGO)
     scale = A.norm_bound * B.norm_bound
     thr_c = max(float(threshold) - CAND_MARGIN * max(scale, 1.0), 0.0)
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
     # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
-    if algo == 2:
-        rows_per_tile = int(rows_per_tile or V2_ROWS)
-        warps = int(warps or V2_WARPS)
-        tile_w = min(int(tile_w or V2_TILE_W), ((n_right + 31) // 32) * 32)
-        smem_optin = ctypes.c_int(0)
-        _lib.check(L.sg_device_info(None, ctypes.byref(smem_optin), None))
-        while warps > 8 and int(L.sg_cossim2_smem_bytes(warps, rows_per_tile, tile_w)) > smem_optin.value:
-            warps -= 8
-    else:
-        tile_w, warps = pick_tile(n_right, tile_w, warps)
+    tile_w, warps = pick_tile(n_right, tile_w, warps)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
     hrank, perm_b, rank_b, bucket_ptr, bucket_dir, post, T = right_side(B, tile_w)
@@ -315,10 +282,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         perm_a = perm_b
     else:
         perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
-    if algo == 2:
-        row_pos, tl_ra, seg_f, seg_start, tile_nseg = left_tiles_v2(A, perm_a, n_rows, rows_per_tile)
     # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
-    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(8 * B.nnz / T, 1))))
+    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
     for attempt in range(3):
         cand_row = _empty(cap, t.int32, dev)
         cand_col = _empty(cap, t.int32, dev)
@@ -328,15 +293,10 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             ev0.record()
         c_count = ctypes.c_void_p(counters.data_ptr())
         c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
-        if algo == 2:
-            _lib.check(L.sg_cossim2_candidates(
-                _ptr(row_pos), _ptr(tl_ra), _ptr(seg_f), _ptr(seg_start), _ptr(tile_nseg), n_rows, _ptr(perm_a),
-                _ptr(bucket_ptr), _ptr(post), A.shape[1], tile_w, tiles_per_group, n_right, _ptr(perm_b), thr_c,
-                _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, rows_per_tile, _stream()))
-        else:
-            _lib.check(L.sg_cossim_candidates(
+        _lib.check(L.sg_cossim_candidates(
                 _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, _ptr(perm_a), n_right,
-                A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, thr_c, tiles_per_group,
+                A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, max(B.norm_bound, 1.0), thr_c,
+                tiles_per_group,
                 _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
         if stats is not None and stats.get("time_kernels"):

@@ -42,17 +42,12 @@ SIGNATURES = {
     "sg_tfidf_vocab_keys": (_i32, [_p, _p, _i32, _p, _p]),
     "sg_num_tiles": (_i64, [_i64, _i32]),
     "sg_postings_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
-    "sg_cossim_candidates": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _f32, _i64, _p, _p,
-                                    _i64, _p, _p, _i32, _p]),
+    "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i32, _i64, _f32, _p, _p, _p, _p, _sz, _p]),
+    "sg_cossim_candidates": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _f32, _f32, _i64, _p,
+                                    _p, _i64, _p, _p, _i32, _p]),
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "sg_left_tiles_workspace_bytes": (_sz, [_i64, _i64]),
-    "sg_left_tiles_build": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "sg_cossim2_smem_bytes": (_sz, [_i32, _i32, _i32]),
-    "sg_cossim2_candidates": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _i64, _p, _f32, _p, _p,
-                                     _i64, _p, _p, _i32, _i32, _p]),
     "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

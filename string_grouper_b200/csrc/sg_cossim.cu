@@ -11,6 +11,7 @@
 //   rescore          exact sorted-merge dot product of every candidate pair
 //   topn_select      strict threshold, top-n per row, value-descending
 #include <cub/cub.cuh>
+#include <cuda_fp16.h>
 
 #include "sg_common.cuh"
 
@@ -39,11 +40,20 @@ __global__ void postings_keys_kernel(int64_t n_rows, const int64_t *__restrict__
     }
 }
 
+// A posting is 4 bytes: the column inside the tile (16 bits) and the weight rounded to fp16 (16 bits).  The
+// candidate scores only have to be within CAND_MARGIN of the exact ones (every candidate is re-scored in the
+// matrix dtype): an fp16 weight is off by at most 2^-11 relative, so a score by at most 4.9e-4.
 __global__ void postings_pack_kernel(int64_t nnz, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     uint2 *__restrict__ post) {
+                                     float w_scale, uint32_t *__restrict__ post) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) post[i] = make_uint2((uint32_t)(keys[i] & 0xffffu), vals[i]);
+    if (i < nnz) {
+        const unsigned h = __half_as_ushort(__float2half_rn(__uint_as_float(vals[i]) * w_scale));
+        post[i] = ((uint32_t)h << 16) | (uint32_t)(keys[i] & 0xffffu);
+    }
 }
+
+__device__ __forceinline__ float post_w(uint32_t e) { return __half2float(__ushort_as_half((unsigned short)(e >> 16))); }
+__device__ __forceinline__ int post_c(uint32_t e) { return (int)(e & 0xffffu); }
 
 // bucket directory: one aligned 8-byte {start, length} per (tile, feature) so that a lane fetches it in one load
 __global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr, int2 *__restrict__ dir) {
@@ -65,8 +75,8 @@ __global__ void __launch_bounds__(NW * 32, min_ctas(NW))
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                          const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
                          const int32_t *__restrict__ perm_a, int64_t n_right, const int2 *__restrict__ bdir,
-                         const uint2 *__restrict__ post, const int32_t *__restrict__ perm_b, int64_t V1, int W,
-                         int64_t T, int64_t tiles_per_group, float thr_c,
+                         const uint32_t *__restrict__ post, const int32_t *__restrict__ perm_b, int64_t V1, int W,
+                         int64_t T, int64_t tiles_per_group, float a_scale, float thr_c,
                          int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
                          unsigned long long cap, unsigned long long *__restrict__ cand_count,
                          unsigned long long *__restrict__ row_queue) {
@@ -108,7 +118,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                 float a = 0.f;
                 if (k < nf) {
                     const int f = a_idx[p0 + k];
-                    a = a_val[p0 + k];
+                    a = a_val[p0 + k] * a_scale;
                     const int2 d = bd[f];
                     b0 = d.x;
                     len = d.y;
@@ -118,9 +128,9 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                 // two lanes may meet on one column, hence the shared-memory atomic.
                 if (len > 0 && len <= SHORT_BUCKET) {
                     for (int j = 0; j < len; ++j) {
-                        const uint2 e = post[b0 + j];
-                        const float x = a * __uint_as_float(e.y);
-                        seen = fmaxf(seen, atomicAdd(acc + e.x, x) + x);
+                        const uint32_t e = post[b0 + j];
+                        const float x = a * post_w(e);
+                        seen = fmaxf(seen, atomicAdd(acc + post_c(e), x) + x);
                     }
                 }
                 __syncwarp();
@@ -135,21 +145,21 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     const float ak = __shfl_sync(FULL, a, src);
                     int p = s + lane;
                     for (; p + 96 < e; p += 128) {
-                        const uint2 e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-                        const float v0 = fmaf(ak, __uint_as_float(e0.y), acc[e0.x]);
-                        acc[e0.x] = v0;
-                        const float v1 = fmaf(ak, __uint_as_float(e1.y), acc[e1.x]);
-                        acc[e1.x] = v1;
-                        const float v2 = fmaf(ak, __uint_as_float(e2.y), acc[e2.x]);
-                        acc[e2.x] = v2;
-                        const float v3 = fmaf(ak, __uint_as_float(e3.y), acc[e3.x]);
-                        acc[e3.x] = v3;
+                        const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
+                        const float v0 = fmaf(ak, post_w(e0), acc[post_c(e0)]);
+                        acc[post_c(e0)] = v0;
+                        const float v1 = fmaf(ak, post_w(e1), acc[post_c(e1)]);
+                        acc[post_c(e1)] = v1;
+                        const float v2 = fmaf(ak, post_w(e2), acc[post_c(e2)]);
+                        acc[post_c(e2)] = v2;
+                        const float v3 = fmaf(ak, post_w(e3), acc[post_c(e3)]);
+                        acc[post_c(e3)] = v3;
                         seen = fmaxf(fmaxf(fmaxf(seen, v0), fmaxf(v1, v2)), v3);
                     }
                     for (; p < e; p += 32) {
-                        const uint2 e0 = post[p];
-                        const float v0 = fmaf(ak, __uint_as_float(e0.y), acc[e0.x]);
-                        acc[e0.x] = v0;
+                        const uint32_t e0 = post[p];
+                        const float v0 = fmaf(ak, post_w(e0), acc[post_c(e0)]);
+                        acc[post_c(e0)] = v0;
                         seen = fmaxf(seen, v0);
                     }
                     __syncwarp();
@@ -380,7 +390,7 @@ size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles)
 }
 
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
-                      const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base,
+                      const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base, float w_scale,
                       int32_t *bucket_ptr, void *bucket_dir, void *postings, void *ws, size_t ws_bytes,
                       void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
@@ -420,8 +430,8 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
         const int bits = 16 + bits_for((uint64_t)(nb - 1));
         SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, nnz, 0,
                                                     bits > 64 ? 64 : bits, st));
-        postings_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted,
-                                                                            (uint2 *)postings);
+        postings_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted, w_scale,
+                                                                            (uint32_t *)postings);
         SG_LAUNCH_CHECK();
     }
     return SG_OK;
@@ -433,7 +443,7 @@ template <int NW>
 static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                              int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
                              int64_t n_cols, const void *bucket_dir, const void *postings,
-                             const int32_t *perm_b, int tile_w, int64_t tiles_per_group,
+                             const int32_t *perm_b, int tile_w, int64_t tiles_per_group, float a_scale,
                              float thr_c, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                              unsigned long long *cand_count, unsigned long long *row_queue, int n_sm,
                              cudaStream_t st) {
@@ -449,8 +459,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, 
     if (ctas < 1) ctas = 1;
     cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
         a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
-        (const uint2 *)postings,
-        perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
+        (const uint32_t *)postings,
+        perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, a_scale, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
         cand_count, row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
@@ -461,7 +471,7 @@ extern "C" {
 int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
                          int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
                          int64_t n_cols, const void *bucket_dir, const void *postings, const int32_t *perm_b,
-                         int tile_w, float cand_threshold,
+                         int tile_w, float a_scale, float cand_threshold,
                          int64_t tiles_per_group, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
                          unsigned long long *cand_count, unsigned long long *row_queue, int warps_per_cta,
                          void *stream_) {
@@ -479,7 +489,7 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, cons
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
         return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right,     \
-                                     n_cols, bucket_dir, postings, perm_b, tile_w, tiles_per_group,          \
+                                     n_cols, bucket_dir, postings, perm_b, tile_w, tiles_per_group, a_scale, \
                                      cand_threshold, cand_row, cand_col, cand_cap, cand_count, row_queue,    \
                                      n_sm, st);
     switch (warps_per_cta) {

@@ -43,7 +43,37 @@ __device__ __forceinline__ uint64_t orderable(double x) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// one thread per row: [lower_bound(row, i), lower_bound(row, i+1)) summed in storage order
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum): fewer than 8 terms are
+// added sequentially, up to 128 with eight interleaved accumulators, longer runs are split recursively.
+// scipy's CSR row sum (`graph.sum(axis=1)`, string_grouper.py:880) is np.add.reduceat over the data array, which
+// yields  data[first] + pairwise_sum(rest);  the 'centroid' representative among IDENTICAL strings is decided by
+// exactly these rounding differences, so the same order of additions is used here.
+__device__ double np_pairwise_sum(const double *a, int64_t n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int64_t i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+}
+
+// one thread per row: segment [lower_bound(row, i), lower_bound(row, i+1)) of the row-sorted list
 __global__ void cc_rowsum_kernel(int64_t n, int64_t nnz, const int32_t *__restrict__ row,
                                  const double *__restrict__ score, const int32_t *__restrict__ label,
                                  double *__restrict__ weight, unsigned long long *__restrict__ best) {
@@ -54,8 +84,17 @@ __global__ void cc_rowsum_kernel(int64_t n, int64_t nnz, const int32_t *__restri
         const int64_t mid = (lo + hi) >> 1;
         if (row[mid] < i) lo = mid + 1; else hi = mid;
     }
-    double s = 0.0;
-    for (int64_t p = lo; p < nnz && row[p] == i; ++p) s = __dadd_rn(s, score[p]);
+    int64_t hi2 = lo;      // upper bound of the segment (rows are contiguous)
+    {
+        int64_t a = lo, b = nnz;
+        while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if (row[mid] <= i) a = mid + 1; else b = mid;
+        }
+        hi2 = a;
+    }
+    const int64_t cnt = hi2 - lo;
+    const double s = cnt == 0 ? 0.0 : (cnt == 1 ? score[lo] : __dadd_rn(score[lo], np_pairwise_sum(score + lo + 1, cnt - 1)));
     weight[i] = s;
     atomicMax(best + label[i], (unsigned long long)orderable(s));
 }

@@ -19,7 +19,7 @@ if len(sys.argv) > 5:
 for algo, tile_w, warps, rows in cfgs:
     st = {"time_kernels": True}
     torch.cuda.synchronize(); t = time.time()
-    got = D.cossim_topn(A, A, 20, 0.8, tile_w=tile_w, warps=warps, stats=st, algo=algo, rows_per_tile=rows or None)
+    got = D.cossim_topn(A, A, 20, 0.8, tile_w=tile_w, warps=warps, stats=st)
     torch.cuda.synchronize(); tk = time.time() - t
     kms = sum(a.elapsed_time(b) for a, b in st["candidate_events"])
     print("algo=%d tile_w=%d warps=%d rows=%d: cossim_topn %.1f ms (candidates kernel %.1f ms), cand=%d nnz=%d -> kernel %.3g MAC/s, %.0f GB/s algorithmic" % (

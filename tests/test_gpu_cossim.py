@@ -14,18 +14,17 @@ def _oracle():
     return pipeline
 
 
-def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, algo=None, rows_per_tile=None):
+def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None):
     from string_grouper_b200 import _device as D
     P = _oracle()
     m, d, _ = P.tf_idf_matrices(master, dupes, dtype=dtype)
     ref = P.build_matches(m, d, None, top_n, thr, n_threads=4)
     A = D.DeviceCSR.from_scipy(m)
     B = A if dupes is None else D.DeviceCSR.from_scipy(d)
-    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps, algo=algo, rows_per_tile=rows_per_tile)
+    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps)
     return m, d, ref, got
 
 
-@pytest.mark.parametrize("algo", [2, 1])
 @pytest.mark.parametrize("n,top_n,thr,dtype", [
     (2000, 20, 0.8, np.float64),
     (2000, 20, 0.8, np.float32),
@@ -33,9 +32,9 @@ def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, a
     (3000, 1, 0.5, np.float64),
     (20000, 20, 0.8, np.float64),
 ])
-def test_self_match_matches_oracle(n, top_n, thr, dtype, algo):
+def test_self_match_matches_oracle(n, top_n, thr, dtype):
     names = make_names(n, seed=1)
-    m, d, ref, got = _run(names, None, top_n, thr, dtype, algo=algo)
+    m, d, ref, got = _run(names, None, top_n, thr, dtype)
     gr, gc, gs = got.host_triples()
     cut = row_cutoffs(ref.indptr, ref.data, top_n, n)
     st = compare_triples(csr_triples(ref), (gr, gc, gs), n, thr, cutoff_row=cut, label="self %d" % n)
@@ -55,17 +54,13 @@ def test_two_series_and_tilings_agree():
     compare_triples(csr_triples(ref), got.host_triples(), len(dupes), 0.7, cutoff_row=cut, label="two-series")
     # block invariance (reference tests test_n_blocks_*): any tile shape gives the same answer
     for tile_w, warps in [(128, 4), (256, 8), (1024, 16), (3072, 16), (1536, 32)]:
-        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps, algo=1)
-        a, b = got.host_triples(), g2.host_triples()
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    for tile_w, warps, rows in [(32, 8, 4), (64, 16, 8), (320, 16, 8), (256, 32, 4), (128, 8, 16), (96, 32, 2)]:
-        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps, algo=2, rows_per_tile=rows)
+        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps)
         a, b = got.host_triples(), g2.host_triples()
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
 
-def test_long_rows_and_tile_lists_beyond_shared_memory():
-    """strings of several hundred characters: tile lists longer than the shared-memory list buffer."""
+def test_long_rows():
+    """strings of several hundred characters (more than 32 features per row: several lane batches)."""
     from string_grouper_b200 import _device as D
     P = _oracle()
     rng = np.random.default_rng(5)
@@ -75,10 +70,9 @@ def test_long_rows_and_tile_lists_beyond_shared_memory():
     m, d, _ = P.tf_idf_matrices(names)
     ref = P.build_matches(m, d, None, 10, 0.5)
     A = D.DeviceCSR.from_scipy(m)
-    for algo in (1, 2):
-        got = D.cossim_topn(A, A, 10, 0.5, algo=algo)
-        cut = row_cutoffs(ref.indptr, ref.data, 10, len(names))
-        compare_triples(csr_triples(ref), got.host_triples(), len(names), 0.5, cutoff_row=cut, label="long rows")
+    got = D.cossim_topn(A, A, 10, 0.5)
+    cut = row_cutoffs(ref.indptr, ref.data, 10, len(names))
+    compare_triples(csr_triples(ref), got.host_triples(), len(names), 0.5, cutoff_row=cut, label="long rows")
 
 
 def test_top_n_larger_than_right_and_empty_rows():
