@@ -314,7 +314,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     if stats is not None:
         stats["n_candidates"] = n_cand
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
-        stats["tiles_per_group"], stats["algo"] = tiles_per_group, algo
+        stats["tiles_per_group"] = tiles_per_group
 
     score = _empty(n_cand, t.float64, dev)
     _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
