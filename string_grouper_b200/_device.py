@@ -16,7 +16,7 @@ _TORCH = None
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0, "order": 0, "tiles": 0, "groups": 0}
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "768"))
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "896"))      # x 32 warps x 4 B = 112 KB: two CTAs per SM
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
