@@ -254,12 +254,16 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        sg = api.StringGrouper(series).fit()
+        sg = api.StringGrouper(series)
+        t1 = time.perf_counter()
+        sg.fit()
+        t2 = time.perf_counter()
         out = sg.get_matches()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if step >= max(1, args.warmup // 2):
             e2e_s.append(dt)
+            e2e_parts = {"validate_s": t1 - t0, "fit_s": t2 - t1, "get_matches_s": t0 + dt - t2}
             e2e_rows = len(out)
             h2d = int(sg._last_stats.get("h2d_bytes", 0))
             d2h = int(len(sg._matches_list) * 16 + 64)
@@ -319,7 +323,7 @@ def main():
                            nnz=A.nnz, vocab=A.shape[1]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "s_per_step": float(np.mean(e2e_s)), "rows": e2e_rows},
+                    "s_per_step": float(np.mean(e2e_s)), "rows": e2e_rows, "last_step_parts": e2e_parts},
             "gpu_launches": launches // args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)

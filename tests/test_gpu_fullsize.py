@@ -66,3 +66,31 @@ def test_full_size_sampled_rows_equal_oracle(fitted):
     st = compare_triples((rr, ref.indices, ref.data), (pos, gc[sel], gs[sel]), N, 0.8, tol=1e-9, cutoff_row=cut,
                          label="663k sample")
     assert st["common"] >= 0.97 * st["pairs_ref"]
+
+
+def test_two_series_large_sampled_rows_equal_oracle():
+    """config-4-shaped run (master x duplicates, min_similarity 0.7) at 400k x 150k."""
+    from oracle.sdt import sp_matmul_topn
+    from parity import compare_triples, row_cutoffs
+    from string_grouper_b200 import StringGrouper
+    base = make_names(480_000, seed=3)
+    master = pd.Series(base[:400_000])
+    dupes = pd.Series(base[380_000:] + make_names(50_000, seed=4))          # 20k shared + 80k + 50k new
+    sg = StringGrouper(master, dupes, min_similarity=0.7).fit()
+    ml = sg._matches_list
+    r, c, s = ml.master_side.to_numpy(), ml.dupe_side.to_numpy(), ml.similarity.to_numpy()
+    assert np.all(np.diff(r) >= 0) and np.all(s > 0.7)
+    same = r[1:] == r[:-1]
+    assert np.all(s[1:][same] <= s[:-1][same])                       # sort=True inside a row
+    assert np.bincount(r).max() <= 20 and c.max() < len(dupes)
+    A, B = sg._get_tf_idf_matrices()
+    fa, fb = A.to_scipy(), B.to_scipy()
+    rows = np.sort(np.random.default_rng(1).choice(len(master), size=1500, replace=False))
+    ref = sp_matmul_topn(fa[rows], fb.T.tocsr(), top_n=20, threshold=0.7, sort=True, n_threads=16)
+    sel = np.isin(r, rows)
+    pos = np.searchsorted(rows, r[sel])
+    cut = row_cutoffs(ref.indptr, ref.data, 20, len(rows))
+    rr = np.repeat(np.arange(len(rows)), np.diff(ref.indptr))
+    st = compare_triples((rr, ref.indices, ref.data), (pos, c[sel], s[sel]), len(dupes), 0.7, tol=1e-9,
+                         cutoff_row=cut, label="400k x 150k sample")
+    assert st["common"] >= 0.97 * st["pairs_ref"] and st["pairs_ref"] > 500
