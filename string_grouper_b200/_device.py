@@ -277,7 +277,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     tile_w, warps = pick_tile(n_right, tile_w, warps)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
-    hrank, perm_b, rank_b, bucket_ptr, bucket_dir, post, T = right_side(B, tile_w)
+    hrank, perm_b, _, _, bucket_dir, post, T = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:

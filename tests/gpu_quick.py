@@ -12,7 +12,7 @@ names = make_names(n, 0)
 t = time.time(); m, d, _ = P.tf_idf_matrices(names, dtype=np.float64); print("oracle tfidf %.2fs nnz=%d V=%d" % (time.time() - t, m.nnz, m.shape[1]))
 macs = P.hot_path_macs(m, m); print("MACs %.4g  (%.3f per pair)" % (macs, macs / n / n))
 A = D.DeviceCSR.from_scipy(m)
-# (algo, tile_w, warps, rows_per_tile)
+# (unused, tile_w, warps, unused)
 cfgs = [(1, 768, 32, 0), (1, 896, 32, 0), (1, 1536, 32, 0), (1, 768, 32, 0)]
 if len(sys.argv) > 5:
     cfgs = [(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))]
