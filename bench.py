@@ -195,7 +195,7 @@ def main():
     names = make_names(args.rows, seed=0)
     n = len(names)
     series = pd.Series(names)
-    data, offsets, flags = _ingest.pack_strings([series])
+    data, offsets, flags, _ = _ingest.pack_strings([series])
     d_bytes, d_off, total = D.upload_strings(data, offsets, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lo, hi = _dist.shard_range(n, rank, world)

@@ -221,6 +221,21 @@ size_t sg_group_reps_workspace_bytes(int64_t n);
 int sg_group_reps(int64_t n, int64_t nnz, const int32_t *row, const int32_t *col, const double *score,
                   int centroid, int32_t *rep /*[dev] n*/, void *ws, size_t ws_bytes, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * String gather for get_matches: replaces `Series.iloc[matches_list.master_side]` /
+ * `.iloc[matches_list.dupe_side]` (sg.py:462, :467) for strings that are resident in HBM as packed UTF-8.
+ * positions[i] is a row of the Series that starts at document `doc_base` of the packed buffer.
+ * sg_gather_offsets: out_offsets[n_sel+1] (the last entry is the total byte count the caller must allocate);
+ * sg_gather_bytes: the bytes.  The pair is a ready-made Arrow large_string array.
+ * ------------------------------------------------------------------------- */
+size_t sg_gather_workspace_bytes(int64_t n_sel);
+int sg_gather_offsets(const int64_t *offsets /*[dev]*/, int64_t doc_base, int64_t n_sel,
+                      const int32_t *positions /*[dev]*/, int64_t *out_offsets /*[dev] n_sel+1*/, void *ws,
+                      size_t ws_bytes, void *stream);
+int sg_gather_bytes(const uint8_t *bytes /*[dev]*/, const int64_t *offsets /*[dev]*/, int64_t doc_base,
+                    int64_t n_sel, const int32_t *positions /*[dev]*/, const int64_t *out_offsets /*[dev]*/,
+                    uint8_t *out_bytes /*[dev]*/, void *stream);
+
 /* row-wise dot of two CSR matrices of equal shape (StringGrouper.dot, sg.py:433-440) */
 int sg_rowwise_dot(int64_t n_rows, const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
                    const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,

@@ -14,7 +14,7 @@ _TORCH = None
 
 # hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
-                 "rowdot": 0, "order": 0, "tiles": 0, "groups": 0}
+                 "rowdot": 0, "order": 0, "tiles": 0, "groups": 0, "gather": 0}
 
 DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "896"))      # x 32 warps x 4 B = 112 KB: two CTAs per SM
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
@@ -377,6 +377,33 @@ def group_reps(M, n, centroid):
     return rep[:n].cpu().numpy().astype(np.int64)
 
 
+class RawStrings:
+    """Packed UTF-8 strings of master ++ duplicates as uploaded for K1, kept for the device string gather."""
+
+    def __init__(self, d_bytes, d_off, n_master, n_docs):
+        self.d_bytes, self.d_off, self.n_master, self.n_docs = d_bytes, d_off, int(n_master), int(n_docs)
+
+
+def gather_strings(raw, doc_base, positions, n_sel):
+    """(offsets int64 [n_sel+1], bytes uint8) on the host of the strings at `positions` (device int32) of the Series
+    starting at document `doc_base`: the `Series.iloc[...]` of get_matches (string_grouper.py:462, :467)."""
+    t = require_cuda()
+    L = _lib.load()
+    dev = raw.d_off.device
+    out_off = _empty(n_sel + 1, t.int64, dev)
+    ws_bytes = int(L.sg_gather_workspace_bytes(n_sel))
+    ws = _empty(ws_bytes, t.uint8, dev)
+    _lib.check(L.sg_gather_offsets(_ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions), _ptr(out_off), _ptr(ws),
+                                   ws_bytes, _stream()))
+    off_host = out_off[:n_sel + 1].cpu().numpy()
+    total = int(off_host[-1])
+    out = _empty(total, t.uint8, dev)
+    _lib.check(L.sg_gather_bytes(_ptr(raw.d_bytes), _ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions),
+                                 _ptr(out_off), _ptr(out), _stream()))
+    LAUNCH_COUNTS["gather"] += 2
+    return off_host, out[:total].cpu().numpy()
+
+
 def matches_from_scipy(m):
     """Upload a host CSR of matches (e.g. returned by a user-supplied _build_matches)."""
     t = require_cuda()
@@ -442,6 +469,7 @@ def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None,
     d_bytes, d_off, total = upload_strings(data, offsets, device)
     if stats is not None:
         stats["h2d_bytes"] = int(total + 8 * len(offsets))
+        stats["raw"] = RawStrings(d_bytes, d_off, n_master, len(offsets) - 1)
     return tfidf_resident(d_bytes, d_off, len(offsets) - 1, total, n_master, ngram, flags, dtype, stats=stats,
                           df_allreduce=df_allreduce, n_docs_fit=n_docs_fit)
 

@@ -72,7 +72,9 @@ def _encode_list(strings):
 def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_to_ascii=True):
     """Concatenate the Series (master, then duplicates) into one ASCII byte buffer.
 
-    Returns (data uint8, offsets int64 [n_total+1], flags for the device analyzer).
+    Returns (data uint8, offsets int64 [n_total+1], flags for the device analyzer, pristine) where `pristine`
+    says that the bytes are the callers' strings verbatim (no host normalisation happened), so the device copy can
+    also serve the string gather of get_matches.
     """
     default_regex = (regex == DEFAULT_REGEX)
     flags = 0
@@ -82,6 +84,7 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
             flags |= SG_FLAG_IGNORE_CASE
     datas, offs = [], []
     base = 0
+    pristine = default_regex
     for s in series_list:
         data, offsets = _arrow_buffers(s)
         n = len(offsets) - 1
@@ -108,6 +111,7 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
                     x = normalize('NFKD', x).encode('ASCII', 'ignore').decode()
                 strings[i] = x
             data, offsets = _encode_list(strings)
+            pristine = False
         if data.size and int(data.max()) >= 0x80:
             raise NotImplementedError(
                 "normalize_to_ascii=False with non-ASCII characters is not supported by the device vectoriser "
@@ -118,7 +122,7 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
     offs.append(np.array([base], dtype=np.int64))
     data = np.concatenate(datas) if len(datas) > 1 else np.ascontiguousarray(datas[0])
     offsets = np.concatenate(offs)
-    return data, offsets, flags
+    return data, offsets, flags, pristine
 
 
 def decode_vocab_keys(keys, ngram):

@@ -138,6 +138,7 @@ class StringGrouper(object):
         self._n_blocks = self._config.n_blocks
         self._vocabulary = None          # device df / rank tables of the last fit (K1)
         self._matches_device = None      # match list in HBM as long as it equals _matches_list
+        self._raw_device = None          # the callers' strings in HBM (packed UTF-8) when ingest left them untouched
         self._last_stats = {}
         self._set_data(master, duplicates, master_id, duplicates_id)
         self._set_options(**kwargs)
@@ -279,7 +280,7 @@ class StringGrouper(object):
             mlo, mhi = _dist.shard_range(n_m, rank, world_size)
             dlo, dhi = _dist.shard_range(n_d, rank, world_size)
             local = [self._master.iloc[mlo:mhi], self._duplicates.iloc[dlo:dhi]]
-            data, offsets, flags = _ingest.pack_strings(local, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+            data, offsets, flags, _ = _ingest.pack_strings(local, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
             master, dup, vocab = _device.tfidf(data, offsets, mhi - mlo, cfg.ngram_size, flags,
                                                cfg.tfidf_matrix_dtype, stats=stats,
                                                df_allreduce=_dist.allreduce_sum_, n_docs_fit=n_m + n_d)
@@ -288,12 +289,17 @@ class StringGrouper(object):
             dup = _device.allgather_csr(dup, n_d)
             master.row_offset, master.global_rows = mlo, n_m
             stats["sharded_vectorise"] = True
+            stats.pop("raw", None)           # only this rank's blocks of the strings are on the device
         else:
-            data, offsets, flags = _ingest.pack_strings(series, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+            data, offsets, flags, pristine = _ingest.pack_strings(series, cfg.regex, cfg.ignore_case,
+                                                                  cfg.normalize_to_ascii)
             master, dup, vocab = _device.tfidf(data, offsets, len(self._master), cfg.ngram_size, flags,
                                                cfg.tfidf_matrix_dtype, stats=stats)
+            if not pristine:
+                stats.pop("raw", None)       # the device bytes are normalised text, not the callers' strings
         self._vocabulary = vocab
         self._last_stats = stats
+        self._raw_device = stats.pop("raw", None)
         return master, (master if dup is None else dup)
 
     def _build_matches(self, master_matrix, duplicate_matrix, n_blocks=None):
@@ -369,8 +375,19 @@ class StringGrouper(object):
         lpos = pairs.master_side.to_numpy()
         rpos = pairs.dupe_side.to_numpy()
         right_strings = self._master if self._duplicates is None else self._duplicates
-        left = _take_side(self._master, lpos, DEFAULT_COLUMN_NAME, ignore_index, LEFT_PREFIX, mirror=False)
-        right = _take_side(right_strings, rpos, DEFAULT_COLUMN_NAME, ignore_index, RIGHT_PREFIX, mirror=True)
+        lvals = rvals = None
+        dev, raw = self._matches_device, self._raw_device
+        if (dev is not None and raw is not None and pairs is self._matches_list and len(pairs) == dev.nnz
+                and _is_arrow_str(self._master) and _is_arrow_str(right_strings)
+                and raw.n_master == len(self._master)):
+            # strings and match positions are both in HBM: gather there, wrap the result as Arrow arrays
+            lvals = _gathered_array(self._master, *_device.gather_strings(raw, 0, dev.d_row, dev.nnz))
+            rbase = 0 if self._duplicates is None else raw.n_master
+            rvals = _gathered_array(right_strings, *_device.gather_strings(raw, rbase, dev.d_col, dev.nnz))
+        left = _take_side(self._master, lpos, DEFAULT_COLUMN_NAME, ignore_index, LEFT_PREFIX, mirror=False,
+                          values=lvals)
+        right = _take_side(right_strings, rpos, DEFAULT_COLUMN_NAME, ignore_index, RIGHT_PREFIX, mirror=True,
+                           values=rvals)
         similarity = pairs.similarity.reset_index(drop=True)
         if self._master_id is None:
             parts = [left, similarity, right]
@@ -598,14 +615,28 @@ class StringGrouper(object):
             raise Exception('Both duplicates and duplicates_id must be pandas.Series of the same length.')
 
 
-def _take_side(series, positions, default_name, drop_index, prefix, mirror):
+def _is_arrow_str(series):
+    return isinstance(series.dtype, pd.StringDtype) and hasattr(series.array, "_pa_array")
+
+
+def _gathered_array(series, offsets, data):
+    """(offsets, bytes) of gathered strings -> an extension array of the Series' own dtype, zero-copy."""
+    import pyarrow as pa
+    n = len(offsets) - 1
+    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
+    return type(series.array)(pa.chunked_array([arr]), dtype=series.dtype)
+
+
+def _take_side(series, positions, default_name, drop_index, prefix, mirror, values=None):
     """Rows of `series` at `positions` as prefixed column(s); index levels become columns unless dropped.
-    `mirror` puts the value column first (right-hand side of get_matches, ref:468)."""
+    `mirror` puts the value column first (right-hand side of get_matches, ref:468).  `values` are the already
+    gathered rows (device string gather) when available."""
     name = series.name if series.name else default_name
     index = series.index
     if drop_index or (index.nlevels == 1 and index.name is None and name != 'index'):
         # fast path (millions of matches): one take on the backing array, one on the index values
-        values = pd.Series(series.array.take(positions), name=f"{prefix}{name}", copy=False)
+        taken = series.array.take(positions) if values is None else values
+        values = pd.Series(taken, name=f"{prefix}{name}", copy=False)
         if drop_index:
             return values
         if isinstance(index, pd.RangeIndex):

@@ -115,3 +115,23 @@ def test_group_representatives_equal_host_rule(group_rep):
     host = sg.get_groups()
     pd.testing.assert_frame_equal(dev, host)
     assert (dev["group_rep_index"] != np.arange(len(names))).sum() > 1000
+
+
+def test_device_string_gather_equals_host_take():
+    """get_matches with the strings gathered on the device (csrc/sg_gather.cu) vs pandas/Arrow take."""
+    import string_grouper_b200 as api
+    master = pd.Series(make_names(20000, seed=71), name="company")
+    dupes = pd.Series(make_names(6000, seed=72) + make_names(20000, seed=71)[:500] + ["", "x"])
+    for args in [(master,), (master, dupes)]:
+        sg = api.StringGrouper(*args, min_similarity=0.75).fit()
+        assert sg._raw_device is not None and sg._matches_device is not None
+        dev = sg.get_matches()
+        sg._raw_device = None
+        host = sg.get_matches()
+        pd.testing.assert_frame_equal(dev, host)
+        assert len(dev) > len(master)
+    # non-ASCII input is normalised on the host: the device copy is not the callers' text, so the host path is taken
+    odd = pd.Series(["Ünited Çorp", "United Corp", "Ünited Çorp."])
+    sg = api.StringGrouper(odd, min_similarity=0.5).fit()
+    assert sg._raw_device is None
+    assert sg.get_matches()["left_side"].tolist()[0] == "Ünited Çorp"
