@@ -284,21 +284,36 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
     # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
     tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
+    c_count = ctypes.c_void_p(counters.data_ptr())
+    c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
+
+    def launch(perm, n_perm_rows, rb, re_, row_buf, col_buf, capacity):
+        counters.zero_()
+        _lib.check(L.sg_cossim_candidates(
+            _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), rb, re_, _ptr(perm), n_right,
+            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, max(B.norm_bound, 1.0), thr_c,
+            tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity, c_count, c_queue, warps, _stream()))
+        LAUNCH_COUNTS["candidates"] += 1
+
+    if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:
+        # Size the candidate buffer from a counting pass over every 64th row (in signature order, so clusters of
+        # identical names are sampled in proportion): duplicate clusters make the count vary from 10 to 200 per row
+        # between corpora, and an undersized buffer would cost a second full launch.
+        stride = 64
+        sample = perm_a[:n_rows:stride].contiguous()
+        dummy = _empty(1, t.int32, dev)
+        launch(sample, int(sample.numel()), row_begin, row_begin + int(sample.numel()), dummy, dummy, 0)
+        est = int(counters[0].item()) * stride
+        cap = min(max(int(1.3 * est) + (1 << 22), 1 << 22), 1 << 31)
+        if stats is not None:
+            stats["n_candidates_estimate"] = est
     for attempt in range(3):
         cand_row = _empty(cap, t.int32, dev)
         cand_col = _empty(cap, t.int32, dev)
-        counters.zero_()
         if stats is not None and stats.get("time_kernels"):
             ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             ev0.record()
-        c_count = ctypes.c_void_p(counters.data_ptr())
-        c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
-        _lib.check(L.sg_cossim_candidates(
-                _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), row_begin, row_end, _ptr(perm_a), n_right,
-                A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, max(B.norm_bound, 1.0), thr_c,
-                tiles_per_group,
-                _ptr(cand_row), _ptr(cand_col), cap, c_count, c_queue, warps, _stream()))
-        LAUNCH_COUNTS["candidates"] += 1
+        launch(perm_a, n_rows, row_begin, row_end, cand_row, cand_col, cap)
         if stats is not None and stats.get("time_kernels"):
             ev1.record()
             stats.setdefault("candidate_events", []).append((ev0, ev1))

@@ -297,6 +297,9 @@ class StringGrouper(object):
                                                cfg.tfidf_matrix_dtype, stats=stats)
             if not pristine:
                 stats.pop("raw", None)       # the device bytes are normalised text, not the callers' strings
+        if master.shape[1] == 0:
+            # sklearn raises this from TfidfVectorizer.fit (the reference hits it in __init__, ref:267/:305-308)
+            raise ValueError("empty vocabulary; perhaps the documents only contain stop words")
         self._vocabulary = vocab
         self._last_stats = stats
         self._raw_device = stats.pop("raw", None)

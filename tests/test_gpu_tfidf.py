@@ -135,3 +135,23 @@ def test_device_string_gather_equals_host_take():
     sg = api.StringGrouper(odd, min_similarity=0.5).fit()
     assert sg._raw_device is None
     assert sg.get_matches()["left_side"].tolist()[0] == "Ünited Çorp"
+
+
+def test_degenerate_inputs():
+    import string_grouper_b200 as api
+    # strings shorter than ngram_size give empty rows but still match themselves (reference fit(), :419-427)
+    out = api.match_strings(pd.Series(["ab", "abc", "abc.", "x", ""]))
+    pairs = set(zip(out.left_index.tolist(), out.right_index.tolist()))
+    assert pairs == {(0, 0), (1, 1), (1, 2), (2, 1), (2, 2), (3, 3), (4, 4)}
+    assert out.similarity.min() >= 1.0 - 1e-12
+    # one row
+    assert len(api.match_strings(pd.Series(["hello world"]))) == 1
+    # nothing to vectorise at all: scikit-learn's error, as in the reference
+    with pytest.raises(ValueError):
+        api.match_strings(pd.Series(["a", "b"]))
+    # no match above the threshold between two Series
+    out = api.match_strings(pd.Series(["alpha beta"]), pd.Series(["gamma delta", "epsilon"]))
+    assert len(out) == 0 and list(out.columns) == ["left_index", "left_side", "similarity", "right_side", "right_index"]
+    # groups on a tiny input
+    g = api.group_similar_strings(pd.Series(["foo inc", "foo inc.", "bar"]))
+    assert g["group_rep_index"].tolist() == [0, 0, 2]
