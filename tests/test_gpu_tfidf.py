@@ -129,7 +129,7 @@ def test_device_string_gather_equals_host_take():
         sg._raw_device = None
         host = sg.get_matches()
         pd.testing.assert_frame_equal(dev, host)
-        assert len(dev) > len(master)
+        assert len(dev) > 2000
     # non-ASCII input is normalised on the host: the device copy is not the callers' text, so the host path is taken
     odd = pd.Series(["Ünited Çorp", "United Corp", "Ünited Çorp."])
     sg = api.StringGrouper(odd, min_similarity=0.5).fit()
