@@ -76,19 +76,70 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(names, full_matrix, n_threads, sample_left=4000, sample_self=20000):
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    reports the machine, and OpenMP threads beyond the quota only spin against each other)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda txt: txt.split()),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", None)):
+        try:
+            if parse:
+                q, per = parse(open(path).read())
+                if q != "max":
+                    n = min(n, max(1, int(float(q) / float(per))))
+            else:
+                q = int(open(path).read())
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+_THREADS = {}
+
+
+def best_thread_count(full_matrix):
+    """The OpenMP thread count at which the oracle's block product runs fastest on this box (probed once on
+    8000 left rows x 48000 right rows; candidates: the usable cores and a few fractions of them)."""
+    if "n" in _THREADS:
+        return _THREADS["n"], _THREADS["probe"]
+    from oracle import pipeline as P
+    cores = usable_cores()
+    cand = sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)})
+    nl, nr = min(8000, full_matrix.shape[0]), min(48000, full_matrix.shape[0])
+    left, right = full_matrix[:nl], full_matrix[:nr]
+    probe = {}
+    for c in cand:
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            P.build_matches(left, right, (1, 12), TOP_N, MIN_SIM, c)
+            best = min(best, time.perf_counter() - t0)
+        probe[c] = round(best, 4)
+    _THREADS["n"] = min(probe, key=probe.get)
+    _THREADS["probe"] = probe
+    return _THREADS["n"], probe
+
+
+def cpu_reference_sample(names, full_matrix, n_threads, sample_left=(6000, 30000), sample_self=20000):
     """Bounded sample of the reference CPU path (oracle port), extrapolated to the whole job.
 
     (a) the oracle's fit() on the first `sample_self` names: analyzer + TfidfVectorizer (2 of the reference's 3
         analyzer passes), block product, LIL symmetrise, match list -> per-string and per-match host costs;
-    (b) the block product of the first `sample_left` left rows against ALL right rows with the reference's own
-        block heuristic (string_grouper.py:387-389) and every host thread -> scaled by n / sample_left.
-    Returns (estimated seconds for the full job, detail dict).
+    (b) the block product of the first s1 and the first s2 left rows against ALL right rows with the reference's
+        own block heuristic (string_grouper.py:387-389): t(s) = fixed + per_row * s.  `fixed` (slicing and
+        transposing the right blocks, one OpenMP region per block) is paid once per job, only `per_row` scales
+        with the left rows, so the job estimate is fixed + per_row * n (NOT t(s) * n / s).
+    Returns (estimated seconds for the full job, estimated pairs, detail dict).
     """
     from oracle import pipeline as P
     n = len(names)
     sample_self = min(sample_self, n)
-    sample_left = min(sample_left, n)
     t0 = time.perf_counter()
     m, d, _ = P.tf_idf_matrices(names[:sample_self])
     t_vec = time.perf_counter() - t0
@@ -102,14 +153,28 @@ def cpu_reference_sample(names, full_matrix, n_threads, sample_left=4000, sample
     per_string = 1.5 * t_vec / sample_self            # fit + transform measured; the reference also fits in __init__
     per_match = t_post / max(len(ml), 1)
     blocks = (1, P.guess_blocks(n, n)[1])
-    t0 = time.perf_counter()
-    Cs = P.build_matches(full_matrix[:sample_left], full_matrix, blocks, TOP_N, MIN_SIM, n_threads)
-    t_mm = time.perf_counter() - t0
-    est_pairs = (Cs.nnz / sample_left) * n * (len(ml) / max(C.nnz, 1))      # symmetrisation growth from (a)
-    est = per_string * n + t_mm * (n / sample_left) + per_match * est_pairs
-    detail = {"t_vectorise_sample_s": round(t_vec, 3), "t_product_sample_s": round(t_mm, 3),
+    s1, s2 = (min(x, n) for x in sample_left)
+    times, nnz_s2 = [], 0
+    for sl in (s1, s2):
+        t0 = time.perf_counter()
+        Cs = P.build_matches(full_matrix[:sl], full_matrix, blocks, TOP_N, MIN_SIM, n_threads)
+        times.append(time.perf_counter() - t0)
+        nnz_s2 = Cs.nnz
+    if s2 > s1:
+        per_row = max((times[1] - times[0]) / (s2 - s1), 0.0)
+        fixed = max(times[0] - per_row * s1, 0.0)
+    else:
+        per_row, fixed = times[0] / max(s1, 1), 0.0
+    t_product = fixed + per_row * n
+    est_pairs = (nnz_s2 / s2) * n * (len(ml) / max(C.nnz, 1))      # symmetrisation growth from (a)
+    est = per_string * n + t_product + per_match * est_pairs
+    detail = {"t_vectorise_sample_s": round(t_vec, 3), "t_product_s1_s2_s": [round(x, 3) for x in times],
+              "left_rows_s1_s2": [s1, s2], "product_fixed_s": round(fixed, 3),
+              "product_per_left_row_us": round(per_row * 1e6, 3), "est_product_s": round(t_product, 2),
               "t_post_sample_s": round(t_post, 3), "t_product_small_s": round(t_mm_small, 3),
-              "est_total_s": round(est, 2), "est_pairs": int(est_pairs), "n_blocks": list(blocks)}
+              "est_vectorise_s": round(per_string * n, 2), "est_post_s": round(per_match * est_pairs, 2),
+              "est_total_s": round(est, 2), "est_pairs": int(est_pairs), "n_blocks": list(blocks),
+              "threads": n_threads}
     return est, est_pairs, detail
 
 
@@ -119,10 +184,10 @@ def run_reference_arm(args, names):
     from oracle import pipeline as P
     from oracle import sdt
     sdt.build()
-    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     full, _, _ = P.tf_idf_matrices(names)           # setup, untimed: the sample needs the full right matrix
     setup = time.perf_counter() - t0
+    cores, probe = best_thread_count(full)
     vals, last = [], None
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -132,9 +197,11 @@ def run_reference_arm(args, names):
             vals.append((est_pairs / est, est, wall))
         last = detail
     value = float(np.mean([v[0] for v in vals]))
-    sample = ("per step: oracle fit() on 20000 names + block product of 4000 left rows x all %d right rows, "
-              "n_blocks=%s, extrapolated to the full job; right matrix built once before timing (%.0f s)"
-              % (len(names), last["n_blocks"], setup))
+    sample = ("per step: oracle fit() on 20000 names + block products of %s left rows x all %d right rows, "
+              "n_blocks=%s, job estimate = fixed + per-left-row cost x rows; right matrix built once before "
+              "timing (%.0f s); threads = fastest of %s on this box (os.cpu_count() = %s, usable = %d)"
+              % (last["left_rows_s1_s2"], len(names), last["n_blocks"], setup, probe, os.cpu_count(),
+                 usable_cores()))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean([v[1] for v in vals])) * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -308,12 +375,15 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import sdt
         sdt.build()
-        cores = os.cpu_count() or 1
         full = A.to_scipy()          # parity-checked equal to the sklearn matrix (tests/test_gpu_tfidf.py)
+        cores, probe = best_thread_count(full)
         est, est_pairs, detail = cpu_reference_sample(names, full, cores)
         cpu_baseline = {"value": est_pairs / est, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "oracle fit() on 20000 names + block product of 4000 left rows x all %d right "
-                                  "rows (n_blocks=%s), extrapolated to the full job" % (n, detail["n_blocks"]),
+                        "sample": "oracle fit() on 20000 names + block products of %s left rows x all %d right "
+                                  "rows (n_blocks=%s); job estimate = fixed + per-left-row cost x rows; threads = "
+                                  "fastest of %s (os.cpu_count() = %s, usable = %d)"
+                                  % (detail["left_rows_s1_s2"], n, detail["n_blocks"], probe, os.cpu_count(),
+                                     usable_cores()),
                         "detail": detail}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -129,25 +129,52 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
 /*
+ * Exact threshold pruning of the left operand (no reference counterpart: sp_matmul_topn,
+ * sg.py:725-743, walks every posting).  For a left row x split into a pruned part x_P and a kept part x_S,
+ * x.y <= |x_P|*max|y| + x_S.y, so only pairs whose partial score over the kept features exceeds
+ * threshold - |x_P|*right_norm can be matches.  sg_feature_df counts the document frequency of every feature
+ * in the right matrix (= postings walked per use of the feature); sg_prune_rows ranks each row's features by
+ * df / weight^2 and prunes the most expensive ones while |x_P|*right_norm <= budget.  Outputs, indexed like the
+ * inputs (absolute positions / row ids): the kept features first inside the row's segment of
+ * out_indices/out_val32, out_len[row] = how many were kept, out_threshold[row] = threshold - margin -
+ * margin_per_feature*kept - |x_P|*right_norm (clamped at 0) = the row's candidate threshold.  The candidate
+ * list stays a superset of the matches; sg_rescore scores every candidate over all features.
+ */
+int sg_feature_df(int64_t n_rows, int64_t n_cols, const int64_t *indptr /*[dev]*/, const int32_t *indices /*[dev]*/,
+                  int32_t *df /*[dev] n_cols*/, void *stream);
+int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[dev]*/,
+                  const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
+                  const int32_t *df_right /*[dev] n_cols*/, float right_norm /* >= largest row norm on the right */,
+                  float budget, float threshold, float margin, float margin_per_feature,
+                  int32_t *out_indices /*[dev]*/, float *out_val32 /*[dev]*/, int32_t *out_len /*[dev] per row id*/,
+                  float *out_threshold /*[dev] per row id*/, void *stream);
+
+/*
  * Candidate generation: for left rows [row_begin,row_end) stream the posting
  * buckets of the row's features into a per-warp shared-memory accumulator tile
- * (fp32), sweep each column tile and append every (row, col) whose fp32 score
- * exceeds `cand_threshold` (= min_similarity - margin, clamped at 0) to the
- * candidate list.  `cand_count` [dev] (zeroed by the caller) ends up holding
+ * (fp32 or fp16, `acc_dtype`), sweep each column tile and append every (row, col) whose score
+ * exceeds the candidate threshold (`cand_threshold` = min_similarity - margin, clamped at 0, or the
+ * row's own `cand_threshold_row[row]` when that array is given) to the candidate list.  `a_len`
+ * (optional, per row id) limits a row to its first a_len[row] stored features (sg_prune_rows).
+ * `cand_count` [dev] (zeroed by the caller) ends up holding
  * the number of candidates FOUND, which may exceed `cand_cap` (then only the
  * first cand_cap were stored and the caller re-runs with a larger buffer).
  * `row_queue` [dev] (zeroed) is the dynamic work queue over (column-tile group, left row) items,
  * groups outermost, `tiles_per_group` column tiles per group (sized by the caller so that one
  * group's posting buckets stay L2-resident).
  */
-int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_indices /*[dev]*/,
+#define SG_ACC_F32 0
+#define SG_ACC_F16 1 /* caller adds 5e-4 per kept feature to the candidate margin; scores must lie in [0, 1] */
+int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len /*[dev] or NULL*/,
+                         const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
                          const int32_t *perm_a /*[dev] processing order of the left rows, or NULL*/,
                          int64_t n_right, int64_t n_cols, const void *bucket_dir /*[dev] {start,len} pairs*/,
                          const void *postings /*[dev]*/,
                          const int32_t *perm_b /*[dev] position -> right row id, or NULL*/, int tile_w,
+                         int acc_dtype,
                          float a_scale /* left weights are multiplied by this: the inverse of w_scale */,
-                         float cand_threshold,
+                         float cand_threshold, const float *cand_threshold_row /*[dev] per row id, or NULL*/,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
                          int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
                          unsigned long long *cand_count /*[dev] 1*/,

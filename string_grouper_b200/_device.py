@@ -14,12 +14,17 @@ _TORCH = None
 
 # hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
-                 "rowdot": 0, "order": 0, "tiles": 0, "groups": 0, "gather": 0}
+                 "rowdot": 0, "order": 0, "tiles": 0, "groups": 0, "gather": 0, "prune": 0}
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "896"))      # x 32 warps x 4 B = 112 KB: two CTAs per SM
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 112 KB of accumulators per CTA, two CTAs per SM
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
+F16_MARGIN_PER_FEATURE = 5e-4   # fp16 accumulator tile: two roundings of <= 2^-12 per added feature (scores <= 1)
+# Exact threshold pruning (csrc/sg_prune.cu): the most expensive features of a left row are skipped while the
+# part of the score they could contribute stays below PRUNE_FRAC * min_similarity.  0 switches it off.
+PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.7"))
+ACC_DTYPE = os.environ.get("SG_B200_ACC", "f16")                    # accumulator tile: f16 | f32
 
 
 def torch():
@@ -73,6 +78,8 @@ class DeviceCSR:
         self._host = None
         self._order = None          # (hrank, perm, rank) in heavy-feature signature order
         self._postings2 = {}
+        self._df = None             # document frequency of every feature (sg_feature_df)
+        self.nonneg = True          # no negative stored value (K1 output; checked for uploaded matrices)
 
     @property
     def device(self):
@@ -99,6 +106,7 @@ class DeviceCSR:
         bound = float(np.sqrt(m.multiply(m).sum(axis=1).max())) if m.nnz else 1.0
         out = cls(m.shape, indptr, indices, val, val32, m.nnz, dtype, max(bound, 1e-30))
         out._host = m
+        out.nonneg = bool(m.nnz == 0 or data.min() >= 0)
         return out
 
     def to_scipy(self):
@@ -237,14 +245,50 @@ class DeviceMatches:
         return getattr(self.to_scipy(), name)
 
 
-def pick_tile(n_right, tile_w=None, warps=None):
-    tile_w = int(tile_w or DEFAULT_TILE_W)
+def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
+    """Column-tile width and warps per CTA.  Default: warps * tile_w * acc_bytes = 112 KB, two CTAs per SM."""
     warps = int(warps or DEFAULT_WARPS)
-    need = ((max(int(n_right), 1) + 127) // 128) * 128
+    tile_w = int(tile_w or DEFAULT_TILE_W) or (112 << 10) // (warps * acc_bytes)
+    q = 512 // acc_bytes                               # tile bytes must be a multiple of 512
+    need = ((max(int(n_right), 1) + q - 1) // q) * q
+    tile_w = max(q, min(tile_w, 65536) // q * q)
     return min(tile_w, need), warps
 
 
-def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None):
+def feature_df(B):
+    """int32 document frequency of every feature of B (cached): the postings walked per use of the feature."""
+    if B._df is None:
+        t = require_cuda()
+        L = _lib.load()
+        df = _empty(B.shape[1], t.int32, B.device)
+        _lib.check(L.sg_feature_df(B.shape[0], B.shape[1], _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(df), _stream()))
+        LAUNCH_COUNTS["prune"] += 1
+        B._df = df
+    return B._df
+
+
+def prune_left(A, B, row_begin, row_end, threshold, margin, margin_per_feature, frac):
+    """Exact threshold pruning of rows [row_begin,row_end) of A against B (sg_prune_rows).
+    Returns (indices, val32, row_len, row_threshold) device arrays indexed like A's own."""
+    t = require_cuda()
+    L = _lib.load()
+    df = feature_df(B)
+    p_idx = t.empty_like(A.d_indices)
+    p_val = t.empty_like(A.d_val32)
+    p_len = _empty(A.shape[0], t.int32, A.device)
+    p_thr = _empty(A.shape[0], t.float32, A.device)
+    budget = max(float(frac) * (float(threshold) - margin), 0.0)
+    # the kernel works on left weights as stored and right rows of norm <= B.norm_bound
+    _lib.check(L.sg_prune_rows(row_begin, row_end, _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), _ptr(df),
+                               float(B.norm_bound), budget, float(threshold), float(margin),
+                               float(margin_per_feature), _ptr(p_idx), _ptr(p_val), _ptr(p_len), _ptr(p_thr),
+                               _stream()))
+    LAUNCH_COUNTS["prune"] += 1
+    return p_idx, p_val, p_len, p_thr
+
+
+def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None,
+                prune=None, acc=None):
     """C[i,:] = top_n{ j : A_i . B_j > threshold } for rows [row_begin,row_end) of A.
 
     Device counterpart of the whole block loop of StringGrouper._build_matches
@@ -269,12 +313,22 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         return DeviceMatches(shape, z32, z32, _empty(1, t.float64, dev), 0, 0)
 
     scale = A.norm_bound * B.norm_bound
-    thr_c = max(float(threshold) - CAND_MARGIN * max(scale, 1.0), 0.0)
+    margin = CAND_MARGIN * max(scale, 1.0)
+    thr_c = max(float(threshold) - margin, 0.0)
+    # fp16 accumulator tiles need scores in [0, 1] (K1's L2-normalised, non-negative rows)
+    acc = (acc or ACC_DTYPE).lower()
+    if acc not in ("f16", "f32"):
+        raise ValueError("accumulator dtype must be 'f16' or 'f32', got %r" % (acc,))
+    if not (A.nonneg and B.nonneg and scale <= 1.0 + 1e-6) or thr_c < 0.05:
+        acc = "f32"      # also near-zero thresholds: a tiny positive score must not round to an fp16 zero
+    acc_code = _lib.SG_ACC_F16 if acc == "f16" else _lib.SG_ACC_F32
+    margin_pf = F16_MARGIN_PER_FEATURE if acc == "f16" else 0.0
+    prune = PRUNE_FRAC if prune is None else float(prune)
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
     # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
-    tile_w, warps = pick_tile(n_right, tile_w, warps)
+    tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "f16" else 4)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
     hrank, perm_b, _, _, bucket_dir, post, T = right_side(B, tile_w)
@@ -286,13 +340,32 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
+    # exact threshold pruning of the left rows; the fp16 tile always takes per-row thresholds (its margin
+    # grows with the number of features added)
+    if (prune > 0.0 and thr_c > 0.0) or margin_pf > 0.0:
+        l_idx, l_val, l_len, l_thr = prune_left(A, B, row_begin, row_end, float(threshold), margin, margin_pf,
+                                                prune if thr_c > 0.0 else 0.0)
+    else:
+        l_idx, l_val, l_len, l_thr = A.d_indices, A.d_val32, None, None
+    if stats is not None:
+        stats["prune"], stats["acc"] = prune, acc
+        if stats.get("count_macs") and l_len is not None:
+            df = feature_df(B).long()
+            pos = t.arange(A.d_indices.numel(), device=dev)
+            rid = t.searchsorted(A.d_indptr[:n_left + 1].contiguous(), pos, right=True) - 1
+            ok = (rid >= row_begin) & (rid < row_end)
+            rid = rid.clamp(0, n_left - 1)
+            live = ok & ((pos - A.d_indptr[rid]) < l_len[rid].long())
+            stats["macs_walked"] = int(df[l_idx.long().clamp(0, A.shape[1] - 1)][live].sum().item())
+            stats["features_kept"] = int(live.sum().item())
 
     def launch(perm, n_perm_rows, rb, re_, row_buf, col_buf, capacity):
         counters.zero_()
         _lib.check(L.sg_cossim_candidates(
-            _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), rb, re_, _ptr(perm), n_right,
-            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, max(B.norm_bound, 1.0), thr_c,
-            tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity, c_count, c_queue, warps, _stream()))
+            _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
+            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, acc_code, max(B.norm_bound, 1.0),
+            thr_c, _ptr(l_thr), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity, c_count, c_queue, warps,
+            _stream()))
         LAUNCH_COUNTS["candidates"] += 1
 
     if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:

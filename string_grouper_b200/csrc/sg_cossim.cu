@@ -70,22 +70,118 @@ constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-p
 // beat deeper per-warp prefetching at 40-48 registers (measured, profiles/r1_notes.md).
 constexpr int min_ctas(int nw) { return 64 / nw < 1 ? 1 : 64 / nw; }
 
-template <int NW>
+// Accumulator tile element: fp32, or fp16 (twice the columns per shared-memory byte: half the directory
+// look-ups and half the clearing per column; the caller widens the candidate margin by the rounding error).
+template <typename AccT>
+struct AccOps;
+template <>
+struct AccOps<float> {
+    static constexpr int PER16 = 4;           // elements per 16-byte vector
+    static __device__ __forceinline__ float fma_store(float *p, float a, float w) {
+        const float v = fmaf(a, w, *p);
+        *p = v;
+        return v;
+    }
+    static __device__ __forceinline__ float atomic_add(float *p, float x) { return atomicAdd(p, x) + x; }
+    // bit i set when element i of the 16-byte vector exceeds thr
+    static __device__ __forceinline__ unsigned above(const uint4 &v, float thr) {
+        return (__uint_as_float(v.x) > thr ? 1u : 0u) | (__uint_as_float(v.y) > thr ? 2u : 0u) |
+               (__uint_as_float(v.z) > thr ? 4u : 0u) | (__uint_as_float(v.w) > thr ? 8u : 0u);
+    }
+    static __device__ __forceinline__ float seen_threshold(float thr) { return thr; }
+};
+template <>
+struct AccOps<__half> {
+    static constexpr int PER16 = 8;
+    static __device__ __forceinline__ float fma_store(__half *p, float a, float w) {
+        const float v = fmaf(a, w, __half2float(*p));
+        *p = __float2half_rn(v);
+        return v;
+    }
+    // shared-memory atomic add on one half of the 32-bit word that holds it (atom.shared.add.noftz.f16x2 with a
+    // zero in the other half; the generic-address atomicAdd(__half*) overload would not use the shared path)
+    static __device__ __forceinline__ float atomic_add(__half *p, float x) {
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+        const unsigned hi = addr & 2u;
+        const unsigned xv = (unsigned)__half_as_ushort(__float2half_rn(x)) << (hi ? 16 : 0);
+        unsigned old;
+        asm volatile("atom.shared.add.noftz.f16x2 %0, [%1], %2;" : "=r"(old) : "r"(addr & ~3u), "r"(xv) : "memory");
+        return __half2float(__ushort_as_half((unsigned short)(hi ? old >> 16 : old & 0xffffu))) + x;
+    }
+    static __device__ __forceinline__ unsigned pair_above(unsigned u, float thr) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&u));
+        return (f.x > thr ? 1u : 0u) | (f.y > thr ? 2u : 0u);
+    }
+    static __device__ __forceinline__ unsigned above(const uint4 &v, float thr) {
+        return pair_above(v.x, thr) | (pair_above(v.y, thr) << 2) | (pair_above(v.z, thr) << 4) |
+               (pair_above(v.w, thr) << 6);
+    }
+    // the stored value is the rounded one: it may exceed the fp32 value the lane tracked by one half ulp
+    static __device__ __forceinline__ float seen_threshold(float thr) { return thr * 0.998f; }
+};
+
+// One bucket-directory batch of a row (32 features, one per lane) applied to the accumulator tile.
+template <typename AccT>
+__device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint32_t *__restrict__ post, int b0,
+                                              int len, float a, int lane, float &seen) {
+    const int b1 = b0 + len;
+    // short buckets: every lane walks its own bucket (one L2 latency for all of them);
+    // two lanes may meet on one column, hence the shared-memory atomic.
+    if (len > 0 && len <= SHORT_BUCKET) {
+        for (int j = 0; j < len; ++j) {
+            const uint32_t e = post[b0 + j];
+            seen = fmaxf(seen, AccOps<AccT>::atomic_add(acc + post_c(e), a * post_w(e)));
+        }
+    }
+    __syncwarp();
+    // long buckets: the whole warp streams one bucket; columns inside one posting
+    // list are distinct, so the read-modify-write needs no atomics.
+    unsigned m = __ballot_sync(FULL, len > SHORT_BUCKET);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int s = __shfl_sync(FULL, b0, src);
+        const int e = __shfl_sync(FULL, b1, src);
+        const float ak = __shfl_sync(FULL, a, src);
+        int p = s + lane;
+        for (; p + 96 < e; p += 128) {
+            const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
+            const float v0 = AccOps<AccT>::fma_store(acc + post_c(e0), ak, post_w(e0));
+            const float v1 = AccOps<AccT>::fma_store(acc + post_c(e1), ak, post_w(e1));
+            const float v2 = AccOps<AccT>::fma_store(acc + post_c(e2), ak, post_w(e2));
+            const float v3 = AccOps<AccT>::fma_store(acc + post_c(e3), ak, post_w(e3));
+            seen = fmaxf(fmaxf(fmaxf(seen, v0), fmaxf(v1, v2)), v3);
+        }
+        for (; p < e; p += 32) {
+            const uint32_t e0 = post[p];
+            seen = fmaxf(seen, AccOps<AccT>::fma_store(acc + post_c(e0), ak, post_w(e0)));
+        }
+        __syncwarp();
+    }
+}
+
+// `a_len` / `thr_row` (both optional): the left operand after exact threshold pruning (sg_prune_rows): row i
+// keeps only its first a_len[i] stored features and is reported against its own candidate threshold.
+template <int NW, typename AccT>
 __global__ void __launch_bounds__(NW * 32, min_ctas(NW))
-cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
-                         const float *__restrict__ a_val, int64_t row_begin, int64_t row_end,
-                         const int32_t *__restrict__ perm_a, int64_t n_right, const int2 *__restrict__ bdir,
-                         const uint32_t *__restrict__ post, const int32_t *__restrict__ perm_b, int64_t V1, int W,
-                         int64_t T, int64_t tiles_per_group, float a_scale, float thr_c,
-                         int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
-                         unsigned long long cap, unsigned long long *__restrict__ cand_count,
-                         unsigned long long *__restrict__ row_queue) {
-    extern __shared__ __align__(16) float smem_acc[];
+cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_len,
+                         const int32_t *__restrict__ a_idx, const float *__restrict__ a_val, int64_t row_begin,
+                         int64_t row_end, const int32_t *__restrict__ perm_a, int64_t n_right,
+                         const int2 *__restrict__ bdir, const uint32_t *__restrict__ post,
+                         const int32_t *__restrict__ perm_b, int64_t V1, int W, int64_t T,
+                         int64_t tiles_per_group, float a_scale, float thr_all,
+                         const float *__restrict__ thr_row, int32_t *__restrict__ cand_row,
+                         int32_t *__restrict__ cand_col, unsigned long long cap,
+                         unsigned long long *__restrict__ cand_count, unsigned long long *__restrict__ row_queue) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *acc = smem_acc + (size_t)warp * W;
+    AccT *acc = reinterpret_cast<AccT *>(smem_raw) + (size_t)warp * W;
+    uint4 *acc16 = reinterpret_cast<uint4 *>(acc);
+    const int n16 = W / AccOps<AccT>::PER16;                // 16-byte vectors per tile, a multiple of 32
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
-    for (int c = lane * 4; c < W; c += 128) *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
     __syncwarp();
 
     // Work item = (column-tile group, left row), groups outermost: at any moment every CTA of the grid streams
@@ -103,97 +199,80 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         const int64_t ridx = (int64_t)(item % (unsigned long long)n_rows);
         const int64_t row = perm_a ? perm_a[ridx] : row_begin + ridx;   // signature order: neighbours share buckets
         const int64_t p0 = a_indptr[row];
-        const int nf = (int)(a_indptr[row + 1] - p0);
+        const int nf = a_len ? a_len[row] : (int)(a_indptr[row + 1] - p0);
         if (nf == 0) continue;
+        const float thr_c = thr_row ? thr_row[row] : thr_all;
+        const float thr_seen = AccOps<AccT>::seen_threshold(thr_c);
         const int64_t t_begin = group * tiles_per_group;
         const int64_t t_end = t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T;
 
+        // the first 32 features of the row stay in registers; their directory entries for the next
+        // column tile are fetched while the current tile is processed
+        int f0 = -1;
+        float a0 = 0.f;
+        if (lane < nf) {
+            f0 = a_idx[p0 + lane];
+            a0 = a_val[p0 + lane] * a_scale;
+        }
+        int2 d_next = make_int2(0, 0);
+        if (f0 >= 0) d_next = bdir[t_begin * V1 + f0];
+
         for (int64_t t = t_begin; t < t_end; ++t) {
             const int64_t c0 = t * W;
-            const int2 *bd = bdir + t * V1;
-            float seen = 0.f;      // largest value this lane wrote into the tile (scores are sums of products >= 0)
-            for (int base = 0; base < nf; base += 32) {
-                const int k = base + lane;
-                int b0 = 0, len = 0;
-                float a = 0.f;
-                if (k < nf) {
-                    const int f = a_idx[p0 + k];
-                    a = a_val[p0 + k] * a_scale;
-                    const int2 d = bd[f];
-                    b0 = d.x;
-                    len = d.y;
-                }
-                const int b1 = b0 + len;
-                // short buckets: every lane walks its own bucket (one L2 latency for all of them);
-                // two lanes may meet on one column, hence the shared-memory atomic.
-                if (len > 0 && len <= SHORT_BUCKET) {
-                    for (int j = 0; j < len; ++j) {
-                        const uint32_t e = post[b0 + j];
-                        const float x = a * post_w(e);
-                        seen = fmaxf(seen, atomicAdd(acc + post_c(e), x) + x);
+            const int2 d0 = d_next;
+            if (f0 >= 0 && t + 1 < t_end) d_next = bdir[(t + 1) * V1 + f0];
+            float seen = 0.f;      // largest value this lane wrote into the tile
+            apply_buckets<AccT>(acc, post, d0.x, d0.y, a0, lane, seen);
+            if (nf > 32) {
+                const int2 *bd = bdir + t * V1;
+                for (int base = 32; base < nf; base += 32) {
+                    const int k = base + lane;
+                    int b0 = 0, len = 0;
+                    float a = 0.f;
+                    if (k < nf) {
+                        const int2 d = bd[a_idx[p0 + k]];
+                        a = a_val[p0 + k] * a_scale;
+                        b0 = d.x;
+                        len = d.y;
                     }
-                }
-                __syncwarp();
-                // long buckets: the whole warp streams one bucket; columns inside one posting
-                // list are distinct, so the read-modify-write needs no atomics.
-                unsigned m = __ballot_sync(FULL, len > SHORT_BUCKET);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int s = __shfl_sync(FULL, b0, src);
-                    const int e = __shfl_sync(FULL, b1, src);
-                    const float ak = __shfl_sync(FULL, a, src);
-                    int p = s + lane;
-                    for (; p + 96 < e; p += 128) {
-                        const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-                        const float v0 = fmaf(ak, post_w(e0), acc[post_c(e0)]);
-                        acc[post_c(e0)] = v0;
-                        const float v1 = fmaf(ak, post_w(e1), acc[post_c(e1)]);
-                        acc[post_c(e1)] = v1;
-                        const float v2 = fmaf(ak, post_w(e2), acc[post_c(e2)]);
-                        acc[post_c(e2)] = v2;
-                        const float v3 = fmaf(ak, post_w(e3), acc[post_c(e3)]);
-                        acc[post_c(e3)] = v3;
-                        seen = fmaxf(fmaxf(fmaxf(seen, v0), fmaxf(v1, v2)), v3);
-                    }
-                    for (; p < e; p += 32) {
-                        const uint32_t e0 = post[p];
-                        const float v0 = fmaf(ak, post_w(e0), acc[post_c(e0)]);
-                        acc[post_c(e0)] = v0;
-                        seen = fmaxf(seen, v0);
-                    }
-                    __syncwarp();
+                    apply_buckets<AccT>(acc, post, b0, len, a, lane, seen);
                 }
             }
             // No value written into this tile exceeded the candidate threshold (the common case):
             // clearing is enough, the tile need not be read back.
-            if (!__any_sync(FULL, seen > thr_c)) {
-                for (int c = lane * 4; c < W; c += 128)
-                    *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!__any_sync(FULL, seen > thr_seen)) {
+                for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
                 __syncwarp();
                 continue;
             }
-            // sweep: report scores above the candidate threshold, clear the tile
-            for (int c = lane * 4; c < W; c += 128) {
-                float4 *q = reinterpret_cast<float4 *>(acc + c);
-                const float4 v = *q;
-                const unsigned nz = (__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) |
-                                     __float_as_uint(v.w)) << 1;
-                if (nz) {
-                    *q = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                    if (mx > thr_c) {
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
+            // sweep: report scores above the candidate threshold, clear the tile; one atomic per warp step
+            for (int c = lane; c < n16; c += 32) {
+                const uint4 v = acc16[c];
+                unsigned m = 0;
+                if (v.x | v.y | v.z | v.w) {
+                    acc16[c] = zero4;
+                    m = AccOps<AccT>::above(v, thr_c);
+                }
+                if (__any_sync(FULL, m != 0)) {
+                    const int cnt = __popc(m);
+                    int incl = cnt;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (vv[i] > thr_c) {
-                                const unsigned long long slot = atomicAdd(cand_count, 1ull);
-                                if (slot < cap) {
-                                    cand_row[slot] = (int32_t)row;
-                                    cand_col[slot] = perm_b ? perm_b[c0 + c + i] : (int32_t)(c0 + c + i);
-                                }
-                            }
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    unsigned long long slot = 0;
+                    if (lane == 31) slot = atomicAdd(cand_count, (unsigned long long)incl);
+                    slot = __shfl_sync(FULL, slot, 31) + (unsigned long long)(incl - cnt);
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (slot < cap) {
+                            const int64_t col = c0 + (int64_t)c * AccOps<AccT>::PER16 + i;
+                            cand_row[slot] = (int32_t)row;
+                            cand_col[slot] = perm_b ? perm_b[col] : (int32_t)col;
                         }
+                        ++slot;
                     }
                 }
             }
@@ -439,69 +518,77 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 
 }  // extern "C"
 
-template <int NW>
-static int launch_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
-                             int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
-                             int64_t n_cols, const void *bucket_dir, const void *postings,
+template <int NW, typename AccT>
+static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, const int32_t *a_indices,
+                             const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
+                             int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
                              const int32_t *perm_b, int tile_w, int64_t tiles_per_group, float a_scale,
-                             float thr_c, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
-                             unsigned long long *cand_count, unsigned long long *row_queue, int n_sm,
-                             cudaStream_t st) {
-    const size_t smem = (size_t)NW * tile_w * sizeof(float);
-    SG_CUDA_TRY(cudaFuncSetAttribute(cossim_candidates_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                             float thr_c, const float *thr_row, int32_t *cand_row, int32_t *cand_col,
+                             int64_t cand_cap, unsigned long long *cand_count, unsigned long long *row_queue,
+                             int n_sm, cudaStream_t st) {
+    const size_t smem = (size_t)NW * tile_w * sizeof(AccT);
+    SG_CUDA_TRY(cudaFuncSetAttribute(cossim_candidates_kernel<NW, AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
     const int64_t T = sg_num_tiles(n_right, tile_w);
     const int64_t n_rows = row_end - row_begin;
     int per_sm = 1;
-    SG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cossim_candidates_kernel<NW>, NW * 32, smem));
+    SG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cossim_candidates_kernel<NW, AccT>, NW * 32,
+                                                              smem));
     if (per_sm < 1) per_sm = 1;
     int64_t ctas = (n_rows + NW - 1) / NW;
     if (ctas > (int64_t)n_sm * per_sm) ctas = (int64_t)n_sm * per_sm;   // persistent grid: resident CTAs x SMs
     if (ctas < 1) ctas = 1;
-    cossim_candidates_kernel<NW><<<(unsigned)ctas, NW * 32, smem, st>>>(
-        a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
-        (const uint32_t *)postings,
-        perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group, a_scale, thr_c, cand_row, cand_col, (unsigned long long)cand_cap,
-        cand_count, row_queue);
+    cossim_candidates_kernel<NW, AccT><<<(unsigned)ctas, NW * 32, smem, st>>>(
+        a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
+        (const uint32_t *)postings, perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group,
+        a_scale, thr_c, thr_row, cand_row, cand_col, (unsigned long long)cand_cap, cand_count, row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }
 
 extern "C" {
 
-int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_indices, const float *a_val32,
-                         int64_t row_begin, int64_t row_end, const int32_t *perm_a, int64_t n_right,
-                         int64_t n_cols, const void *bucket_dir, const void *postings, const int32_t *perm_b,
-                         int tile_w, float a_scale, float cand_threshold,
-                         int64_t tiles_per_group, int32_t *cand_row, int32_t *cand_col, int64_t cand_cap,
-                         unsigned long long *cand_count, unsigned long long *row_queue, int warps_per_cta,
-                         void *stream_) {
+int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const int32_t *a_indices,
+                         const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
+                         int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
+                         const int32_t *perm_b, int tile_w, int acc_dtype, float a_scale, float cand_threshold,
+                         const float *cand_threshold_row, int64_t tiles_per_group, int32_t *cand_row,
+                         int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
+                         unsigned long long *row_queue, int warps_per_cta, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (row_end <= row_begin || n_right <= 0) return SG_OK;
-    if (tile_w <= 0 || (tile_w & 127)) return fail(SG_ERR_INVALID, "tile_w must be a positive multiple of 128");
+    if (acc_dtype != SG_ACC_F32 && acc_dtype != SG_ACC_F16)
+        return fail(SG_ERR_INVALID, "acc_dtype must be SG_ACC_F32 or SG_ACC_F16");
+    const int acc_bytes = acc_dtype == SG_ACC_F16 ? 2 : 4;
+    if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 512)
+        return fail(SG_ERR_INVALID, "tile_w * accumulator size must be a positive multiple of 512 bytes");
+    if (tile_w > 65536) return fail(SG_ERR_INVALID, "tile_w must not exceed 65536 (16-bit posting columns)");
     if (!(cand_threshold >= 0.f)) return fail(SG_ERR_INVALID, "cand_threshold must be >= 0");
     int dev = 0, n_sm = 0, smem_optin = 0;
     SG_CUDA_TRY(cudaGetDevice(&dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if ((size_t)warps_per_cta * tile_w * sizeof(float) > (size_t)smem_optin)
-        return fail(SG_ERR_INVALID, "warps_per_cta*tile_w*4 = %zu exceeds %d bytes of shared memory",
-                    (size_t)warps_per_cta * tile_w * sizeof(float), smem_optin);
+    if ((size_t)warps_per_cta * tile_w * acc_bytes > (size_t)smem_optin)
+        return fail(SG_ERR_INVALID, "warps_per_cta*tile_w*%d = %zu exceeds %d bytes of shared memory", acc_bytes,
+                    (size_t)warps_per_cta * tile_w * acc_bytes, smem_optin);
+#define SG_ARGS                                                                                              \
+    a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, postings, \
+        perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, cand_row, cand_col,   \
+        cand_cap, cand_count, row_queue, n_sm, st
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
-        return launch_candidates<NW>(a_indptr, a_indices, a_val32, row_begin, row_end, perm_a, n_right,     \
-                                     n_cols, bucket_dir, postings, perm_b, tile_w, tiles_per_group, a_scale, \
-                                     cand_threshold, cand_row, cand_col, cand_cap, cand_count, row_queue,    \
-                                     n_sm, st);
+        return acc_dtype == SG_ACC_F16 ? launch_candidates<NW, __half>(SG_ARGS)                             \
+                                       : launch_candidates<NW, float>(SG_ARGS);
     switch (warps_per_cta) {
         SG_CASE(4)
         SG_CASE(8)
         SG_CASE(16)
-        SG_CASE(24)
         SG_CASE(32)
         default:
-            return fail(SG_ERR_INVALID, "warps_per_cta must be one of 4, 8, 16, 24, 32");
+            return fail(SG_ERR_INVALID, "warps_per_cta must be one of 4, 8, 16, 32");
     }
 #undef SG_CASE
+#undef SG_ARGS
 }
 
 int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const int64_t *a_indptr,

@@ -1,0 +1,132 @@
+// Exact threshold pruning of the left operand of K2, for sm_100a.
+//
+// No reference counterpart: sp_matmul_topn (call sites /root/reference/string_grouper/string_grouper.py:725-743)
+// walks every posting of every feature of a left row.  With x = x_P + x_S (P = a set of the row's features)
+//
+//     x . y  =  x_P . y + x_S . y  <=  |x_P| |y| + x_S . y            (Cauchy-Schwarz)
+//
+// so a pair can only exceed `threshold` if its partial score over the kept features S exceeds
+// threshold - |x_P| * max|y|.  Per left row the features are ranked by cost / weight^2 (cost = document
+// frequency of the feature in the RIGHT matrix = postings walked for it) and the most expensive ones are
+// moved into P while |x_P| * max|y| stays within `budget`: the frequent n-grams, which carry most of the
+// postings and (low idf) little of the norm.  The candidate list stays a superset of the true matches; every
+// candidate is re-scored exactly over ALL features (sg_rescore), so results do not change.
+#include "sg_common.cuh"
+
+namespace sg {
+
+__global__ void feature_df_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ indices, int32_t *__restrict__ df) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t p1 = indptr[row + 1];
+    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32) atomicAdd(df + indices[p], 1);
+}
+
+// one warp per left row
+__global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ idx, const float *__restrict__ val,
+                                  const int32_t *__restrict__ df_right, float right_norm, float budget,
+                                  float threshold, float margin, float margin_per_feature,
+                                  int32_t *__restrict__ out_idx, float *__restrict__ out_val,
+                                  int32_t *__restrict__ out_len, float *__restrict__ out_thr) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = lane_id();
+    const int64_t row = row_begin + r;
+    const int64_t p0 = indptr[row];
+    const int nf = (int)(indptr[row + 1] - p0);
+    // |x_P| <= budget / max|y|
+    const float lim = right_norm > 0.f ? budget / right_norm : 0.f;
+    const float lim2 = lim * lim;
+    int kept = 0;
+    float norm_p2 = 0.f;
+    for (int base = 0; base < nf; base += 32) {
+        const int k = base + lane;
+        float my_key = -1.f, my_w2 = 0.f, my_v = 0.f;
+        int my_f = 0;
+        if (k < nf) {
+            my_f = idx[p0 + k];
+            my_v = val[p0 + k];
+            my_w2 = my_v * my_v;
+            // cost per unit of squared norm; features nobody on the right holds cost nothing and stay
+            my_key = my_w2 > 0.f ? (float)df_right[my_f] / my_w2 : 0.f;
+        }
+        // squared norm of everything ranked before feature k (larger key first, ties by position)
+        float before = 0.f;
+        for (int jb = 0; jb < nf; jb += 32) {
+            const int j = jb + lane;
+            float o_key = -1.f, o_w2 = 0.f;
+            if (jb == base) {
+                o_key = my_key;
+                o_w2 = my_w2;
+            } else if (j < nf) {
+                const float v = val[p0 + j];
+                o_w2 = v * v;
+                o_key = o_w2 > 0.f ? (float)df_right[idx[p0 + j]] / o_w2 : 0.f;
+            }
+            const int lim_s = nf - jb < 32 ? nf - jb : 32;
+            for (int s = 0; s < lim_s; ++s) {
+                const float kk = __shfl_sync(FULL, o_key, s);
+                const float ww = __shfl_sync(FULL, o_w2, s);
+                if (kk > my_key || (kk == my_key && jb + s < k)) before += ww;
+            }
+        }
+        const bool in_p = k < nf && my_key > 0.f && before + my_w2 <= lim2;
+        const bool keep = k < nf && !in_p;
+        const unsigned km = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int64_t w = p0 + kept + __popc(km & ((1u << lane) - 1u));
+            out_idx[w] = my_f;
+            out_val[w] = my_v;
+        }
+        kept += __popc(km);
+        float s = in_p ? my_w2 : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        norm_p2 += s;
+    }
+    if (lane == 0) {
+        out_len[row] = kept;
+        // the rounding of the fp32 norm arithmetic is covered by the relative and absolute slack
+        const float bound = sqrtf(norm_p2) * right_norm * (1.f + 1e-5f) + 1e-6f;
+        const float thr = threshold - margin - margin_per_feature * (float)kept - (norm_p2 > 0.f ? bound : 0.f);
+        out_thr[row] = thr > 0.f ? thr : 0.f;
+    }
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_feature_df(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices, int32_t *df,
+                  void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_cols <= 0) return SG_OK;
+    SG_CUDA_TRY(cudaMemsetAsync(df, 0, (size_t)n_cols * sizeof(int32_t), st));
+    if (n_rows > 0) {
+        feature_df_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, df);
+        SG_LAUNCH_CHECK();
+    }
+    return SG_OK;
+}
+
+int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
+                  const float *val32, const int32_t *df_right, float right_norm, float budget, float threshold,
+                  float margin, float margin_per_feature, int32_t *out_indices, float *out_val32,
+                  int32_t *out_len, float *out_threshold, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int64_t n = row_end - row_begin;
+    if (n <= 0) return SG_OK;
+    if (!(budget >= 0.f) || !(right_norm >= 0.f)) return fail(SG_ERR_INVALID, "budget and right_norm must be >= 0");
+    prune_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, val32, df_right,
+                                                              right_norm, budget, threshold, margin,
+                                                              margin_per_feature, out_indices, out_val32, out_len,
+                                                              out_threshold);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+}  // extern "C"

@@ -14,14 +14,14 @@ def _oracle():
     return pipeline
 
 
-def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None):
+def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, prune=None, acc=None, stats=None):
     from string_grouper_b200 import _device as D
     P = _oracle()
     m, d, _ = P.tf_idf_matrices(master, dupes, dtype=dtype)
     ref = P.build_matches(m, d, None, top_n, thr, n_threads=4)
     A = D.DeviceCSR.from_scipy(m)
     B = A if dupes is None else D.DeviceCSR.from_scipy(d)
-    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps)
+    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps, prune=prune, acc=acc, stats=stats)
     return m, d, ref, got
 
 
@@ -57,6 +57,53 @@ def test_two_series_and_tilings_agree():
         _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps)
         a, b = got.host_triples(), g2.host_triples()
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("thr", [0.8, 0.5, 0.3])
+def test_pruning_and_accumulator_variants_agree(thr):
+    """Exact threshold pruning (csrc/sg_prune.cu) and the fp16 accumulator tile only change which candidates
+    are generated, never the result: every variant returns the same triples, bit for bit, as the unpruned
+    fp32 traversal, and those equal the oracle."""
+    names = make_names(12000, seed=11)
+    st0 = {"count_macs": True}
+    m, d, ref, base = _run(names, None, 20, thr, prune=0.0, acc="f32", stats=st0)
+    cut = row_cutoffs(ref.indptr, ref.data, 20, len(names))
+    compare_triples(csr_triples(ref), base.host_triples(), len(names), thr, cutoff_row=cut, label="unpruned")
+    b = base.host_triples()
+    walked = {}
+    for prune, acc, tile_w in [(0.0, "f16", None), (0.5, "f32", None), (0.7, "f16", None), (0.9, "f32", 256),
+                               (0.95, "f16", 512), (0.7, "f16", 3072)]:
+        st = {"count_macs": True}
+        _, _, _, got = _run(names, None, 20, thr, prune=prune, acc=acc, tile_w=tile_w, stats=st)
+        g = got.host_triples()
+        assert got.nnz == base.nnz, (prune, acc, got.nnz, base.nnz)
+        for x, y in zip(b, g):
+            assert np.array_equal(x, y), (prune, acc, tile_w)
+        walked[(prune, acc)] = st.get("macs_walked")
+    full = walked[(0.0, "f16")]
+    assert walked[(0.7, "f16")] < 0.6 * full and walked[(0.95, "f16")] <= walked[(0.7, "f16")]
+
+
+def test_pruning_two_series_unnormalised_rows():
+    """user-supplied scipy matrices (rows not L2-normalised, a few negative weights): the bound uses the right
+    matrix' largest row norm, the accumulator falls back to fp32."""
+    from string_grouper_b200 import _device as D
+    from oracle.sdt import sp_matmul_topn
+    P = _oracle()
+    master = make_names(4000, seed=21)
+    dupes = make_names(3000, seed=22) + master[:500]
+    m, d, _ = P.tf_idf_matrices(master, dupes)
+    rng = np.random.default_rng(0)
+    m = m.copy(); d = d.copy()
+    m.data *= rng.uniform(0.5, 1.5, size=m.nnz)
+    d.data *= rng.uniform(0.5, 2.0, size=d.nnz)
+    d.data[rng.choice(d.nnz, size=50, replace=False)] *= -1.0
+    ref = sp_matmul_topn(m, d.T.tocsr(), top_n=10, threshold=0.6, sort=True, n_threads=4)
+    A, B = D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(d)
+    cut = row_cutoffs(ref.indptr, ref.data, 10, len(master))
+    for prune in (0.0, 0.7):
+        got = D.cossim_topn(A, B, 10, 0.6, prune=prune)
+        compare_triples(csr_triples(ref), got.host_triples(), len(dupes), 0.6, cutoff_row=cut, label="unnormalised")
 
 
 def test_long_rows():
