@@ -131,30 +131,42 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 /*
  * Exact threshold pruning of the left operand (no reference counterpart: sp_matmul_topn,
  * sg.py:725-743, walks every posting).  For a left row x split into a pruned part x_P and a kept part x_S,
- * x.y <= |x_P|*max|y| + x_S.y, so only pairs whose partial score over the kept features exceeds
- * threshold - |x_P|*right_norm can be matches.  sg_feature_df counts the document frequency of every feature
- * in the right matrix (= postings walked per use of the feature); sg_prune_rows ranks each row's features by
- * df / weight^2 and prunes the most expensive ones while |x_P|*right_norm <= budget.  Outputs, indexed like the
- * inputs (absolute positions / row ids): the kept features first inside the row's segment of
- * out_indices/out_val32, out_len[row] = how many were kept, out_threshold[row] = threshold - margin -
- * margin_per_feature*kept - |x_P|*right_norm (clamped at 0) = the row's candidate threshold.  The candidate
- * list stays a superset of the matches; sg_rescore scores every candidate over all features.
+ * x.y <= |x_P|*|y_P| + x_S.y, so only pairs whose partial score over the kept features exceeds
+ * threshold - |x_P|*|y_P| can be matches.  sg_feature_df counts the document frequency of every feature
+ * in the right matrix (= postings walked per use of the feature); sg_prune_rows ranks each row's prunable
+ * features (`prunable[f] >= 0`, NULL = all) by df / weight^2 and prunes the most expensive ones while
+ * |x_P|*right_norm <= budget.  Outputs, indexed like the inputs (absolute positions / row ids): the kept
+ * features first inside the row's segment of out_indices/out_val32, out_len[row] = how many were kept,
+ * out_threshold[row] = threshold - margin - margin_per_feature*kept (clamped at 0), out_pruned_norm[row] = |x_P|
+ * rounded up.  With the prunable set = the heavy features of sg_heavy_features, |y_P| <= |y_H|:
+ * sg_heavy_norms gives |y_H| per right row (rounded up), sg_row_order sorts the right rows by its quantisation
+ * first, and sg_tile_bounds the largest |y_H| per column tile of that order; sg_cossim_candidates reports
+ * (row i, column j of tile t) when the partial score exceeds out_threshold[i] - out_pruned_norm[i]*bound[t].
+ * The candidate list stays a superset of the matches; sg_rescore scores every candidate over all features.
  */
 int sg_feature_df(int64_t n_rows, int64_t n_cols, const int64_t *indptr /*[dev]*/, const int32_t *indices /*[dev]*/,
                   int32_t *df /*[dev] n_cols*/, void *stream);
 int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[dev]*/,
                   const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
-                  const int32_t *df_right /*[dev] n_cols*/, float right_norm /* >= largest row norm on the right */,
+                  const int32_t *df_right /*[dev] n_cols*/, const int8_t *prunable /*[dev] n_cols or NULL*/,
+                  float right_norm /* >= largest row norm on the right */,
                   float budget, float threshold, float margin, float margin_per_feature,
                   int32_t *out_indices /*[dev]*/, float *out_val32 /*[dev]*/, int32_t *out_len /*[dev] per row id*/,
-                  float *out_threshold /*[dev] per row id*/, void *stream);
+                  float *out_threshold /*[dev] per row id*/, float *out_pruned_norm /*[dev] per row id*/,
+                  void *stream);
+int sg_heavy_norms(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[dev]*/,
+                   const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/, const int8_t *hrank /*[dev]*/,
+                   float *out_norm /*[dev] row_end-row_begin*/, void *stream);
+int sg_tile_bounds(int64_t n_right, const int32_t *perm /*[dev] position -> row, or NULL*/,
+                   const float *row_norm /*[dev] per row*/, int tile_w, float *bound /*[dev] n_tiles*/, void *stream);
 
 /*
  * Candidate generation: for left rows [row_begin,row_end) stream the posting
  * buckets of the row's features into a per-warp shared-memory accumulator tile
- * (fp32 or fp16, `acc_dtype`), sweep each column tile and append every (row, col) whose score
+ * (fp32 or 16-bit fixed point, `acc_dtype`), sweep each column tile and append every (row, col) whose score
  * exceeds the candidate threshold (`cand_threshold` = min_similarity - margin, clamped at 0, or the
- * row's own `cand_threshold_row[row]` when that array is given) to the candidate list.  `a_len`
+ * row's own `cand_threshold_row[row]` when that array is given, lowered by pruned_norm_row[row] *
+ * tile_bound[tile] when those are given) to the candidate list.  `a_len`
  * (optional, per row id) limits a row to its first a_len[row] stored features (sg_prune_rows).
  * `cand_count` [dev] (zeroed by the caller) ends up holding
  * the number of candidates FOUND, which may exceed `cand_cap` (then only the
@@ -164,7 +176,7 @@ int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[d
  * group's posting buckets stay L2-resident).
  */
 #define SG_ACC_F32 0
-#define SG_ACC_F16 1 /* caller adds 5e-4 per kept feature to the candidate margin; scores must lie in [0, 1] */
+#define SG_ACC_U16 1 /* 1/32768 fixed point: caller adds 2e-5 per kept feature to the margin; weights >= 0, scores < 2 */
 int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len /*[dev] or NULL*/,
                          const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
@@ -175,6 +187,8 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len
                          int acc_dtype,
                          float a_scale /* left weights are multiplied by this: the inverse of w_scale */,
                          float cand_threshold, const float *cand_threshold_row /*[dev] per row id, or NULL*/,
+                         const float *pruned_norm_row /*[dev] per row id, or NULL*/,
+                         const float *tile_bound /*[dev] per column tile; required with pruned_norm_row*/,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
                          int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
                          unsigned long long *cand_count /*[dev] 1*/,
@@ -218,9 +232,12 @@ size_t sg_order_workspace_bytes(int64_t n_rows, int64_t n_cols);
 /* hrank[n_cols] int8: rank among the n_heavy (<= 64) most frequent features of the matrix, else -1 */
 int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices, int n_heavy,
                       int8_t *hrank /*[dev]*/, void *ws, size_t ws_bytes, void *stream);
-/* perm[i] = id of the i-th row of [row_begin,row_end) in signature order; rank = inverse (relative ids) */
+/* perm[i] = id of the i-th row of [row_begin,row_end) in signature order; rank = inverse (relative ids).
+ * With `row_norm` (per row of the range, sg_heavy_norms) the 5-bit quantisation of row_norm*norm_scale leads the
+ * sort key, so that rows of similar heavy norm share column tiles (see sg_tile_bounds). */
 int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
-                 const int8_t *hrank, int32_t *perm /*[dev]*/, int32_t *rank /*[dev] or NULL*/, void *ws,
+                 const int8_t *hrank, const float *row_norm /*[dev] or NULL*/, float norm_scale,
+                 int32_t *perm /*[dev]*/, int32_t *rank /*[dev] or NULL*/, void *ws,
                  size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *

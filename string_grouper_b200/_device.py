@@ -20,11 +20,11 @@ DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 112 KB 
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
-F16_MARGIN_PER_FEATURE = 5e-4   # fp16 accumulator tile: two roundings of <= 2^-12 per added feature (scores <= 1)
-# Exact threshold pruning (csrc/sg_prune.cu): the most expensive features of a left row are skipped while the
-# part of the score they could contribute stays below PRUNE_FRAC * min_similarity.  0 switches it off.
+U16_MARGIN_PER_FEATURE = 2e-5   # 1/32768 fixed-point accumulator tile: one rounding of <= 2^-16 per added product
+# Exact threshold pruning (csrc/sg_prune.cu): the most expensive heavy features of a left row are skipped while
+# their norm times the largest right-row norm stays below PRUNE_FRAC * min_similarity.  0 switches it off.
 PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.7"))
-ACC_DTYPE = os.environ.get("SG_B200_ACC", "f16")                    # accumulator tile: f16 | f32
+ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulator tile: u16 | f32
 
 
 def torch():
@@ -79,6 +79,7 @@ class DeviceCSR:
         self._order = None          # (hrank, perm, rank) in heavy-feature signature order
         self._postings2 = {}
         self._df = None             # document frequency of every feature (sg_feature_df)
+        self._heavy_norm = None     # per-row norm over the heavy features (sg_heavy_norms)
         self.nonneg = True          # no negative stored value (K1 output; checked for uploaded matrices)
 
     @property
@@ -151,8 +152,20 @@ def heavy_features(B):
     return hrank
 
 
-def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True):
-    """(perm, rank) of rows [row_begin,row_end) of M sorted by heavy-feature signature."""
+def heavy_norms(M, hrank, row_begin=0, row_end=None):
+    """fp32 norm of rows [row_begin,row_end) of M over the heavy features, rounded up (sg_heavy_norms)."""
+    t = require_cuda()
+    L = _lib.load()
+    row_end = M.shape[0] if row_end is None else row_end
+    out = _empty(max(row_end - row_begin, 0), t.float32, M.device)
+    _lib.check(L.sg_heavy_norms(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(M.d_val32),
+                                _ptr(hrank), _ptr(out), _stream()))
+    LAUNCH_COUNTS["prune"] += 1
+    return out
+
+
+def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True, row_norm=None, norm_scale=1.0):
+    """(perm, rank) of rows [row_begin,row_end) of M sorted by (quantised heavy norm,) heavy-feature signature."""
     t = require_cuda()
     L = _lib.load()
     row_end = M.shape[0] if row_end is None else row_end
@@ -161,8 +174,8 @@ def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True):
     rank = _empty(n, t.int32, M.device) if want_rank else None
     ws_bytes = int(L.sg_order_workspace_bytes(max(n, 1), M.shape[1]))
     ws = _empty(ws_bytes, t.uint8, M.device)
-    _lib.check(L.sg_row_order(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(hrank), _ptr(perm),
-                              _ptr(rank), _ptr(ws), ws_bytes, _stream()))
+    _lib.check(L.sg_row_order(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(hrank), _ptr(row_norm),
+                              float(norm_scale), _ptr(perm), _ptr(rank), _ptr(ws), ws_bytes, _stream()))
     LAUNCH_COUNTS["order"] += 2
     return perm, rank
 
@@ -173,7 +186,8 @@ def right_side(B, tile_w):
     L = _lib.load()
     if B._order is None:
         hrank = heavy_features(B)
-        perm, rank = row_order(B, hrank)
+        B._heavy_norm = heavy_norms(B, hrank)
+        perm, rank = row_order(B, hrank, row_norm=B._heavy_norm, norm_scale=1.0 / max(B.norm_bound, 1e-30))
         B._order = (hrank, perm, rank)
     hrank, perm, rank = B._order
     if tile_w not in B._postings2:
@@ -192,7 +206,10 @@ def right_side(B, tile_w):
                                        _ptr(bucket_dir), _ptr(post),
                                        _ptr(ws), ws_bytes, _stream()))
         LAUNCH_COUNTS["postings"] += 3
-        B._postings2[tile_w] = (bucket_ptr, bucket_dir, post, T)
+        bound = _empty(T, t.float32, B.device)
+        _lib.check(L.sg_tile_bounds(n_rows, _ptr(perm), _ptr(B._heavy_norm), tile_w, _ptr(bound), _stream()))
+        LAUNCH_COUNTS["prune"] += 1
+        B._postings2[tile_w] = (bucket_ptr, bucket_dir, post, T, bound)
     return (hrank, perm, rank) + B._postings2[tile_w]
 
 
@@ -267,9 +284,10 @@ def feature_df(B):
     return B._df
 
 
-def prune_left(A, B, row_begin, row_end, threshold, margin, margin_per_feature, frac):
-    """Exact threshold pruning of rows [row_begin,row_end) of A against B (sg_prune_rows).
-    Returns (indices, val32, row_len, row_threshold) device arrays indexed like A's own."""
+def prune_left(A, B, hrank, row_begin, row_end, threshold, margin, margin_per_feature, frac):
+    """Exact threshold pruning of rows [row_begin,row_end) of A against B (sg_prune_rows); only B's heavy
+    features (hrank >= 0) are prunable.  Returns (indices, val32, row_len, row_threshold, pruned_norm) device
+    arrays indexed like A's own."""
     t = require_cuda()
     L = _lib.load()
     df = feature_df(B)
@@ -277,14 +295,15 @@ def prune_left(A, B, row_begin, row_end, threshold, margin, margin_per_feature, 
     p_val = t.empty_like(A.d_val32)
     p_len = _empty(A.shape[0], t.int32, A.device)
     p_thr = _empty(A.shape[0], t.float32, A.device)
+    p_xp = _empty(A.shape[0], t.float32, A.device)
     budget = max(float(frac) * (float(threshold) - margin), 0.0)
     # the kernel works on left weights as stored and right rows of norm <= B.norm_bound
     _lib.check(L.sg_prune_rows(row_begin, row_end, _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), _ptr(df),
-                               float(B.norm_bound), budget, float(threshold), float(margin),
+                               _ptr(hrank), float(B.norm_bound), budget, float(threshold), float(margin),
                                float(margin_per_feature), _ptr(p_idx), _ptr(p_val), _ptr(p_len), _ptr(p_thr),
-                               _stream()))
+                               _ptr(p_xp), _stream()))
     LAUNCH_COUNTS["prune"] += 1
-    return p_idx, p_val, p_len, p_thr
+    return p_idx, p_val, p_len, p_thr, p_xp
 
 
 def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None,
@@ -315,23 +334,23 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     scale = A.norm_bound * B.norm_bound
     margin = CAND_MARGIN * max(scale, 1.0)
     thr_c = max(float(threshold) - margin, 0.0)
-    # fp16 accumulator tiles need scores in [0, 1] (K1's L2-normalised, non-negative rows)
+    # fixed-point accumulator tiles need non-negative weights and scores below 2 (K1's L2-normalised rows)
     acc = (acc or ACC_DTYPE).lower()
-    if acc not in ("f16", "f32"):
-        raise ValueError("accumulator dtype must be 'f16' or 'f32', got %r" % (acc,))
+    if acc not in ("u16", "f32"):
+        raise ValueError("accumulator dtype must be 'u16' or 'f32', got %r" % (acc,))
     if not (A.nonneg and B.nonneg and scale <= 1.0 + 1e-6) or thr_c < 0.05:
-        acc = "f32"      # also near-zero thresholds: a tiny positive score must not round to an fp16 zero
-    acc_code = _lib.SG_ACC_F16 if acc == "f16" else _lib.SG_ACC_F32
-    margin_pf = F16_MARGIN_PER_FEATURE if acc == "f16" else 0.0
+        acc = "f32"      # also near-zero thresholds: a tiny positive score must not round to a fixed-point zero
+    acc_code = _lib.SG_ACC_U16 if acc == "u16" else _lib.SG_ACC_F32
+    margin_pf = U16_MARGIN_PER_FEATURE if acc == "u16" else 0.0
     prune = PRUNE_FRAC if prune is None else float(prune)
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
     # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
-    tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "f16" else 4)
+    tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
-    hrank, perm_b, _, _, bucket_dir, post, T = right_side(B, tile_w)
+    hrank, perm_b, _, _, bucket_dir, post, T, tile_bound = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:
@@ -340,13 +359,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
-    # exact threshold pruning of the left rows; the fp16 tile always takes per-row thresholds (its margin
-    # grows with the number of features added)
+    # exact threshold pruning of the left rows; the fixed-point tile always takes per-row thresholds (its
+    # margin grows with the number of features added)
     if (prune > 0.0 and thr_c > 0.0) or margin_pf > 0.0:
-        l_idx, l_val, l_len, l_thr = prune_left(A, B, row_begin, row_end, float(threshold), margin, margin_pf,
-                                                prune if thr_c > 0.0 else 0.0)
+        l_idx, l_val, l_len, l_thr, l_xp = prune_left(A, B, hrank, row_begin, row_end, float(threshold), margin,
+                                                      margin_pf, prune if thr_c > 0.0 else 0.0)
     else:
-        l_idx, l_val, l_len, l_thr = A.d_indices, A.d_val32, None, None
+        l_idx, l_val, l_len, l_thr, l_xp = A.d_indices, A.d_val32, None, None, None
     if stats is not None:
         stats["prune"], stats["acc"] = prune, acc
         if stats.get("count_macs") and l_len is not None:
@@ -364,8 +383,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         _lib.check(L.sg_cossim_candidates(
             _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
             A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, acc_code, max(B.norm_bound, 1.0),
-            thr_c, _ptr(l_thr), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity, c_count, c_queue, warps,
-            _stream()))
+            thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity,
+            c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
 
     if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:

@@ -22,7 +22,7 @@ SG_FLAG_STRIP_DEFAULT = 2
 SG_SYMM_FIX_DIAGONAL = 1
 SG_SYMM_MIRROR = 2
 SG_ACC_F32 = 0
-SG_ACC_F16 = 1
+SG_ACC_U16 = 1
 
 _i64 = ctypes.c_int64
 _i32 = ctypes.c_int
@@ -46,12 +46,14 @@ SIGNATURES = {
     "sg_postings_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i32, _i64, _f32, _p, _p, _p, _p, _sz, _p]),
     "sg_feature_df": (_i32, [_i64, _i64, _p, _p, _p, _p]),
-    "sg_prune_rows": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p]),
+    "sg_prune_rows": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p]),
+    "sg_heavy_norms": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "sg_tile_bounds": (_i32, [_i64, _p, _p, _i32, _p, _p]),
     "sg_cossim_candidates": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i32, _f32, _f32,
-                                    _p, _i64, _p, _p, _i64, _p, _p, _i32, _p]),
+                                    _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _i32, _p]),
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
-    "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _sz, _p]),
     "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -70,72 +70,82 @@ constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-p
 // beat deeper per-warp prefetching at 40-48 registers (measured, profiles/r1_notes.md).
 constexpr int min_ctas(int nw) { return 64 / nw < 1 ? 1 : 64 / nw; }
 
-// Accumulator tile element: fp32, or fp16 (twice the columns per shared-memory byte: half the directory
-// look-ups and half the clearing per column; the caller widens the candidate margin by the rounding error).
+// Accumulator tile element.
+//   float    : fp32 scores, read-modify-write in the long-bucket path, CAS-loop atomics in the short one.
+//   uint16_t : 16-bit fixed point (1/32768 units, scores in [0, 2)), two columns per 32-bit word, every update
+//              one native integer ATOMS.ADD on the word.  Twice the columns per shared-memory byte: half the
+//              directory look-ups and half the clearing per column.  Each product is rounded once (<= 2^-16),
+//              sums are exact; the caller widens the candidate margin by 2e-5 per kept feature.
+constexpr float FIX_ONE = 32768.f;
+
 template <typename AccT>
 struct AccOps;
 template <>
 struct AccOps<float> {
+    typedef float val_t;
     static constexpr int PER16 = 4;           // elements per 16-byte vector
-    static __device__ __forceinline__ float fma_store(float *p, float a, float w) {
-        const float v = fmaf(a, w, *p);
-        *p = v;
+    static __device__ __forceinline__ float left_weight(float a) { return a; }
+    static __device__ __forceinline__ float threshold(float thr) { return thr; }
+    static __device__ __forceinline__ float fma_store(float *acc, int col, float a, float w) {
+        const float v = fmaf(a, w, acc[col]);
+        acc[col] = v;
         return v;
     }
-    static __device__ __forceinline__ float atomic_add(float *p, float x) { return atomicAdd(p, x) + x; }
+    static __device__ __forceinline__ float atomic_add(float *acc, int col, float a, float w) {
+        const float x = a * w;
+        return atomicAdd(acc + col, x) + x;
+    }
+    static __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
     // bit i set when element i of the 16-byte vector exceeds thr
     static __device__ __forceinline__ unsigned above(const uint4 &v, float thr) {
         return (__uint_as_float(v.x) > thr ? 1u : 0u) | (__uint_as_float(v.y) > thr ? 2u : 0u) |
                (__uint_as_float(v.z) > thr ? 4u : 0u) | (__uint_as_float(v.w) > thr ? 8u : 0u);
     }
-    static __device__ __forceinline__ float seen_threshold(float thr) { return thr; }
 };
 template <>
-struct AccOps<__half> {
+struct AccOps<uint16_t> {
+    typedef int val_t;
     static constexpr int PER16 = 8;
-    static __device__ __forceinline__ float fma_store(__half *p, float a, float w) {
-        const float v = fmaf(a, w, __half2float(*p));
-        *p = __float2half_rn(v);
-        return v;
+    static __device__ __forceinline__ float left_weight(float a) { return a * FIX_ONE; }
+    // v > floor(thr * 32768)  <=>  v / 32768 > thr  for integer v
+    static __device__ __forceinline__ int threshold(float thr) { return (int)floorf(thr * FIX_ONE); }
+    static __device__ __forceinline__ int atomic_add(uint16_t *acc, int col, float a, float w) {
+        const int x = __float2int_rn(a * w);
+        const unsigned sh = ((unsigned)col & 1u) << 4;
+        const unsigned old = atomicAdd(reinterpret_cast<unsigned *>(acc) + (col >> 1), (unsigned)x << sh);
+        return (int)((old >> sh) & 0xffffu) + x;
     }
-    // shared-memory atomic add on one half of the 32-bit word that holds it (atom.shared.add.noftz.f16x2 with a
-    // zero in the other half; the generic-address atomicAdd(__half*) overload would not use the shared path)
-    static __device__ __forceinline__ float atomic_add(__half *p, float x) {
-        const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
-        const unsigned hi = addr & 2u;
-        const unsigned xv = (unsigned)__half_as_ushort(__float2half_rn(x)) << (hi ? 16 : 0);
-        unsigned old;
-        asm volatile("atom.shared.add.noftz.f16x2 %0, [%1], %2;" : "=r"(old) : "r"(addr & ~3u), "r"(xv) : "memory");
-        return __half2float(__ushort_as_half((unsigned short)(hi ? old >> 16 : old & 0xffffu))) + x;
+    static __device__ __forceinline__ int fma_store(uint16_t *acc, int col, float a, float w) {
+        return atomic_add(acc, col, a, w);
     }
-    static __device__ __forceinline__ unsigned pair_above(unsigned u, float thr) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&u));
-        return (f.x > thr ? 1u : 0u) | (f.y > thr ? 2u : 0u);
+    static __device__ __forceinline__ int vmax(int a, int b) { return max(a, b); }
+    static __device__ __forceinline__ unsigned pair_above(unsigned u, int thr) {
+        return ((int)(u & 0xffffu) > thr ? 1u : 0u) | ((int)(u >> 16) > thr ? 2u : 0u);
     }
-    static __device__ __forceinline__ unsigned above(const uint4 &v, float thr) {
+    static __device__ __forceinline__ unsigned above(const uint4 &v, int thr) {
         return pair_above(v.x, thr) | (pair_above(v.y, thr) << 2) | (pair_above(v.z, thr) << 4) |
                (pair_above(v.w, thr) << 6);
     }
-    // the stored value is the rounded one: it may exceed the fp32 value the lane tracked by one half ulp
-    static __device__ __forceinline__ float seen_threshold(float thr) { return thr * 0.998f; }
 };
 
 // One bucket-directory batch of a row (32 features, one per lane) applied to the accumulator tile.
 template <typename AccT>
 __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint32_t *__restrict__ post, int b0,
-                                              int len, float a, int lane, float &seen) {
+                                              int len, float a, int lane,
+                                              typename AccOps<AccT>::val_t &seen) {
+    typedef AccOps<AccT> Ops;
     const int b1 = b0 + len;
     // short buckets: every lane walks its own bucket (one L2 latency for all of them);
     // two lanes may meet on one column, hence the shared-memory atomic.
     if (len > 0 && len <= SHORT_BUCKET) {
         for (int j = 0; j < len; ++j) {
             const uint32_t e = post[b0 + j];
-            seen = fmaxf(seen, AccOps<AccT>::atomic_add(acc + post_c(e), a * post_w(e)));
+            seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e), a, post_w(e)));
         }
     }
     __syncwarp();
     // long buckets: the whole warp streams one bucket; columns inside one posting
-    // list are distinct, so the read-modify-write needs no atomics.
+    // list are distinct, so the fp32 read-modify-write needs no atomics.
     unsigned m = __ballot_sync(FULL, len > SHORT_BUCKET);
     while (m) {
         const int src = __ffs(m) - 1;
@@ -146,22 +156,24 @@ __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint
         int p = s + lane;
         for (; p + 96 < e; p += 128) {
             const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-            const float v0 = AccOps<AccT>::fma_store(acc + post_c(e0), ak, post_w(e0));
-            const float v1 = AccOps<AccT>::fma_store(acc + post_c(e1), ak, post_w(e1));
-            const float v2 = AccOps<AccT>::fma_store(acc + post_c(e2), ak, post_w(e2));
-            const float v3 = AccOps<AccT>::fma_store(acc + post_c(e3), ak, post_w(e3));
-            seen = fmaxf(fmaxf(fmaxf(seen, v0), fmaxf(v1, v2)), v3);
+            const typename Ops::val_t v0 = Ops::fma_store(acc, post_c(e0), ak, post_w(e0));
+            const typename Ops::val_t v1 = Ops::fma_store(acc, post_c(e1), ak, post_w(e1));
+            const typename Ops::val_t v2 = Ops::fma_store(acc, post_c(e2), ak, post_w(e2));
+            const typename Ops::val_t v3 = Ops::fma_store(acc, post_c(e3), ak, post_w(e3));
+            seen = Ops::vmax(Ops::vmax(Ops::vmax(seen, v0), Ops::vmax(v1, v2)), v3);
         }
         for (; p < e; p += 32) {
             const uint32_t e0 = post[p];
-            seen = fmaxf(seen, AccOps<AccT>::fma_store(acc + post_c(e0), ak, post_w(e0)));
+            seen = Ops::vmax(seen, Ops::fma_store(acc, post_c(e0), ak, post_w(e0)));
         }
         __syncwarp();
     }
 }
 
-// `a_len` / `thr_row` (both optional): the left operand after exact threshold pruning (sg_prune_rows): row i
-// keeps only its first a_len[i] stored features and is reported against its own candidate threshold.
+// Pruned left operand (sg_prune_rows; all three optional together): row i keeps only its first a_len[i] stored
+// features; a pair (i, j) is reported when its partial score exceeds
+//     thr_row[i] - xp_norm[i] * tile_bound[tile of j]
+// = the row's threshold minus what the pruned features can still add for the columns of that tile.
 template <int NW, typename AccT>
 __global__ void __launch_bounds__(NW * 32, min_ctas(NW))
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_len,
@@ -170,15 +182,18 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                          const int2 *__restrict__ bdir, const uint32_t *__restrict__ post,
                          const int32_t *__restrict__ perm_b, int64_t V1, int W, int64_t T,
                          int64_t tiles_per_group, float a_scale, float thr_all,
-                         const float *__restrict__ thr_row, int32_t *__restrict__ cand_row,
+                         const float *__restrict__ thr_row, const float *__restrict__ xp_norm,
+                         const float *__restrict__ tile_bound, int32_t *__restrict__ cand_row,
                          int32_t *__restrict__ cand_col, unsigned long long cap,
                          unsigned long long *__restrict__ cand_count, unsigned long long *__restrict__ row_queue) {
+    typedef AccOps<AccT> Ops;
+    typedef typename Ops::val_t val_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     AccT *acc = reinterpret_cast<AccT *>(smem_raw) + (size_t)warp * W;
     uint4 *acc16 = reinterpret_cast<uint4 *>(acc);
-    const int n16 = W / AccOps<AccT>::PER16;                // 16-byte vectors per tile, a multiple of 32
+    const int n16 = W / Ops::PER16;                         // 16-byte vectors per tile, a multiple of 32
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
     for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
@@ -201,8 +216,8 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         const int64_t p0 = a_indptr[row];
         const int nf = a_len ? a_len[row] : (int)(a_indptr[row + 1] - p0);
         if (nf == 0) continue;
-        const float thr_c = thr_row ? thr_row[row] : thr_all;
-        const float thr_seen = AccOps<AccT>::seen_threshold(thr_c);
+        const float thr_r = thr_row ? thr_row[row] : thr_all;
+        const float xp = xp_norm ? xp_norm[row] : 0.f;
         const int64_t t_begin = group * tiles_per_group;
         const int64_t t_end = t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T;
 
@@ -212,7 +227,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         float a0 = 0.f;
         if (lane < nf) {
             f0 = a_idx[p0 + lane];
-            a0 = a_val[p0 + lane] * a_scale;
+            a0 = Ops::left_weight(a_val[p0 + lane] * a_scale);
         }
         int2 d_next = make_int2(0, 0);
         if (f0 >= 0) d_next = bdir[t_begin * V1 + f0];
@@ -221,7 +236,8 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
             const int64_t c0 = t * W;
             const int2 d0 = d_next;
             if (f0 >= 0 && t + 1 < t_end) d_next = bdir[(t + 1) * V1 + f0];
-            float seen = 0.f;      // largest value this lane wrote into the tile
+            const val_t thr_c = Ops::threshold(xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r);
+            val_t seen = 0;        // largest value this lane wrote into the tile
             apply_buckets<AccT>(acc, post, d0.x, d0.y, a0, lane, seen);
             if (nf > 32) {
                 const int2 *bd = bdir + t * V1;
@@ -231,7 +247,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     float a = 0.f;
                     if (k < nf) {
                         const int2 d = bd[a_idx[p0 + k]];
-                        a = a_val[p0 + k] * a_scale;
+                        a = Ops::left_weight(a_val[p0 + k] * a_scale);
                         b0 = d.x;
                         len = d.y;
                     }
@@ -240,7 +256,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
             }
             // No value written into this tile exceeded the candidate threshold (the common case):
             // clearing is enough, the tile need not be read back.
-            if (!__any_sync(FULL, seen > thr_seen)) {
+            if (!__any_sync(FULL, seen > thr_c)) {
                 for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
                 __syncwarp();
                 continue;
@@ -251,7 +267,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                 unsigned m = 0;
                 if (v.x | v.y | v.z | v.w) {
                     acc16[c] = zero4;
-                    m = AccOps<AccT>::above(v, thr_c);
+                    m = Ops::above(v, thr_c);
                 }
                 if (__any_sync(FULL, m != 0)) {
                     const int cnt = __popc(m);
@@ -268,7 +284,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                         const int i = __ffs(m) - 1;
                         m &= m - 1;
                         if (slot < cap) {
-                            const int64_t col = c0 + (int64_t)c * AccOps<AccT>::PER16 + i;
+                            const int64_t col = c0 + (int64_t)c * Ops::PER16 + i;
                             cand_row[slot] = (int32_t)row;
                             cand_col[slot] = perm_b ? perm_b[col] : (int32_t)col;
                         }
@@ -523,7 +539,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
                              const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
                              int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
                              const int32_t *perm_b, int tile_w, int64_t tiles_per_group, float a_scale,
-                             float thr_c, const float *thr_row, int32_t *cand_row, int32_t *cand_col,
+                             float thr_c, const float *thr_row, const float *xp_norm, const float *tile_bound,
+                             int32_t *cand_row, int32_t *cand_col,
                              int64_t cand_cap, unsigned long long *cand_count, unsigned long long *row_queue,
                              int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)NW * tile_w * sizeof(AccT);
@@ -541,7 +558,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
     cossim_candidates_kernel<NW, AccT><<<(unsigned)ctas, NW * 32, smem, st>>>(
         a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
         (const uint32_t *)postings, perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group,
-        a_scale, thr_c, thr_row, cand_row, cand_col, (unsigned long long)cand_cap, cand_count, row_queue);
+        a_scale, thr_c, thr_row, xp_norm, tile_bound, cand_row, cand_col, (unsigned long long)cand_cap, cand_count,
+        row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }
@@ -552,14 +570,16 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
                          const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
                          int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
                          const int32_t *perm_b, int tile_w, int acc_dtype, float a_scale, float cand_threshold,
-                         const float *cand_threshold_row, int64_t tiles_per_group, int32_t *cand_row,
+                         const float *cand_threshold_row, const float *pruned_norm_row, const float *tile_bound,
+                         int64_t tiles_per_group, int32_t *cand_row,
                          int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
                          unsigned long long *row_queue, int warps_per_cta, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (row_end <= row_begin || n_right <= 0) return SG_OK;
-    if (acc_dtype != SG_ACC_F32 && acc_dtype != SG_ACC_F16)
-        return fail(SG_ERR_INVALID, "acc_dtype must be SG_ACC_F32 or SG_ACC_F16");
-    const int acc_bytes = acc_dtype == SG_ACC_F16 ? 2 : 4;
+    if (acc_dtype != SG_ACC_F32 && acc_dtype != SG_ACC_U16)
+        return fail(SG_ERR_INVALID, "acc_dtype must be SG_ACC_F32 or SG_ACC_U16");
+    if (pruned_norm_row && !tile_bound) return fail(SG_ERR_INVALID, "pruned_norm_row needs tile_bound");
+    const int acc_bytes = acc_dtype == SG_ACC_U16 ? 2 : 4;
     if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 512)
         return fail(SG_ERR_INVALID, "tile_w * accumulator size must be a positive multiple of 512 bytes");
     if (tile_w > 65536) return fail(SG_ERR_INVALID, "tile_w must not exceed 65536 (16-bit posting columns)");
@@ -573,11 +593,11 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
                     (size_t)warps_per_cta * tile_w * acc_bytes, smem_optin);
 #define SG_ARGS                                                                                              \
     a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, postings, \
-        perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, cand_row, cand_col,   \
-        cand_cap, cand_count, row_queue, n_sm, st
+        perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, pruned_norm_row,      \
+        tile_bound, cand_row, cand_col, cand_cap, cand_count, row_queue, n_sm, st
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
-        return acc_dtype == SG_ACC_F16 ? launch_candidates<NW, __half>(SG_ARGS)                             \
+        return acc_dtype == SG_ACC_U16 ? launch_candidates<NW, uint16_t>(SG_ARGS)                           \
                                        : launch_candidates<NW, float>(SG_ARGS);
     switch (warps_per_cta) {
         SG_CASE(4)

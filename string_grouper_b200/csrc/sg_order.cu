@@ -41,8 +41,13 @@ __global__ void order_hrank_fill_kernel(const int32_t *__restrict__ sorted_cols,
     if (i < n_heavy) hrank[sorted_cols[i]] = (int8_t)i;
 }
 
+// `row_norm` (optional): the row's norm over the heavy features (sg_heavy_norms).  Its 5-bit quantisation becomes
+// the most significant part of the sort key (the 5 least frequent signature bits make room), so that the rows of
+// a column tile have similar heavy norms: the per-tile bound of the pruned traversal (sg_tile_bounds) is then
+// close to the bound of each column.
 __global__ void order_signature_kernel(int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ indptr,
                                        const int32_t *__restrict__ indices, const int8_t *__restrict__ hrank,
+                                       const float *__restrict__ row_norm, float norm_scale,
                                        uint64_t *__restrict__ sig, int32_t *__restrict__ ids) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -56,6 +61,11 @@ __global__ void order_signature_kernel(int64_t row_begin, int64_t n_rows, const 
 #pragma unroll
     for (int o = 16; o; o >>= 1) s |= __shfl_xor_sync(FULL, s, o);
     if (lane_id() == 0) {
+        if (row_norm) {
+            int q = (int)ceilf(row_norm[r] * norm_scale * 31.f);
+            q = q < 0 ? 0 : (q > 31 ? 31 : q);
+            s = ((uint64_t)q << 59) | (s >> 5);
+        }
         sig[r] = s;
         ids[r] = (int32_t)row;
     }
@@ -119,7 +129,8 @@ int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, con
 
 // perm[i] = id of the i-th row of [row_begin, row_end) in signature order; rank = inverse (relative to row_begin).
 int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
-                 const int8_t *hrank, int32_t *perm, int32_t *rank, void *ws, size_t ws_bytes, void *stream_) {
+                 const int8_t *hrank, const float *row_norm, float norm_scale, int32_t *perm, int32_t *rank,
+                 void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t n = row_end - row_begin;
     if (n <= 0) return SG_OK;
@@ -131,7 +142,8 @@ int sg_row_order(int64_t row_begin, int64_t row_end, const int64_t *indptr, cons
     cub::DeviceRadixSort::SortPairs(nullptr, b2, sig, sig_sorted, ids, perm, n);
     char *tmp = ar.take<char>(b2);
     if (!ar.ok()) return fail(SG_ERR_INVALID, "order workspace too small (%zu < %zu)", ws_bytes, ar.off);
-    order_signature_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, hrank, sig, ids);
+    order_signature_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, hrank, row_norm,
+                                                                   norm_scale, sig, ids);
     SG_LAUNCH_CHECK();
     SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, b2, sig, sig_sorted, ids, perm, n, 0, 64, st));
     if (rank) {

@@ -11,6 +11,12 @@
 // moved into P while |x_P| * max|y| stays within `budget`: the frequent n-grams, which carry most of the
 // postings and (low idf) little of the norm.  The candidate list stays a superset of the true matches; every
 // candidate is re-scored exactly over ALL features (sg_rescore), so results do not change.
+//
+// Tighter, per column tile: when P only holds features of a fixed set H (the 64 most frequent features of the
+// right matrix, sg_heavy_features),  x_P . y = x_P . y_H <= |x_P| |y_H|,  and |y_H| (sg_heavy_norms) is well
+// below |y| for most rows.  The right rows are ordered by quantised |y_H| first (sg_row_order), so the
+// largest |y_H| inside a column tile (sg_tile_bounds) is close to that of each of its columns and the
+// candidate threshold of (row i, tile t) becomes  threshold - |x_P(i)| * bound(t).
 #include "sg_common.cuh"
 
 namespace sg {
@@ -26,10 +32,12 @@ __global__ void feature_df_kernel(int64_t n_rows, const int64_t *__restrict__ in
 // one warp per left row
 __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ indptr,
                                   const int32_t *__restrict__ idx, const float *__restrict__ val,
-                                  const int32_t *__restrict__ df_right, float right_norm, float budget,
+                                  const int32_t *__restrict__ df_right, const int8_t *__restrict__ prunable,
+                                  float right_norm, float budget,
                                   float threshold, float margin, float margin_per_feature,
                                   int32_t *__restrict__ out_idx, float *__restrict__ out_val,
-                                  int32_t *__restrict__ out_len, float *__restrict__ out_thr) {
+                                  int32_t *__restrict__ out_len, float *__restrict__ out_thr,
+                                  float *__restrict__ out_xp) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     const int lane = lane_id();
@@ -49,8 +57,9 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
             my_f = idx[p0 + k];
             my_v = val[p0 + k];
             my_w2 = my_v * my_v;
-            // cost per unit of squared norm; features nobody on the right holds cost nothing and stay
-            my_key = my_w2 > 0.f ? (float)df_right[my_f] / my_w2 : 0.f;
+            // cost per unit of squared norm; features nobody on the right holds cost nothing and stay,
+            // and so do features outside the prunable set (key 0 = never pruned)
+            my_key = (my_w2 > 0.f && (!prunable || prunable[my_f] >= 0)) ? (float)df_right[my_f] / my_w2 : 0.f;
         }
         // squared norm of everything ranked before feature k (larger key first, ties by position)
         float before = 0.f;
@@ -62,8 +71,9 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
                 o_w2 = my_w2;
             } else if (j < nf) {
                 const float v = val[p0 + j];
+                const int f = idx[p0 + j];
                 o_w2 = v * v;
-                o_key = o_w2 > 0.f ? (float)df_right[idx[p0 + j]] / o_w2 : 0.f;
+                o_key = (o_w2 > 0.f && (!prunable || prunable[f] >= 0)) ? (float)df_right[f] / o_w2 : 0.f;
             }
             const int lim_s = nf - jb < 32 ? nf - jb : 32;
             for (int s = 0; s < lim_s; ++s) {
@@ -89,9 +99,47 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
     if (lane == 0) {
         out_len[row] = kept;
         // the rounding of the fp32 norm arithmetic is covered by the relative and absolute slack
-        const float bound = sqrtf(norm_p2) * right_norm * (1.f + 1e-5f) + 1e-6f;
-        const float thr = threshold - margin - margin_per_feature * (float)kept - (norm_p2 > 0.f ? bound : 0.f);
+        const float xp = norm_p2 > 0.f ? sqrtf(norm_p2) * (1.f + 1e-5f) + 1e-6f : 0.f;
+        const float thr = threshold - margin - margin_per_feature * (float)kept;
         out_thr[row] = thr > 0.f ? thr : 0.f;
+        out_xp[row] = xp;
+    }
+}
+
+// norm of every row restricted to the heavy features (hrank >= 0), rounded up; one warp per row
+__global__ void heavy_norms_kernel(int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ indptr,
+                                   const int32_t *__restrict__ idx, const float *__restrict__ val,
+                                   const int8_t *__restrict__ hrank, float *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int64_t row = row_begin + r;
+    const int64_t p1 = indptr[row + 1];
+    float s = 0.f;
+    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32)
+        if (hrank[idx[p]] >= 0) s = fmaf(val[p], val[p], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane_id() == 0) out[r] = s > 0.f ? sqrtf(s) * (1.f + 1e-5f) + 1e-6f : 0.f;
+}
+
+// bound[t] = largest heavy norm among the right rows at positions [t*W, (t+1)*W) of the processing order
+__global__ void tile_bounds_kernel(int64_t n_right, const int32_t *__restrict__ perm,
+                                   const float *__restrict__ row_norm, int W, float *__restrict__ bound) {
+    const int64_t t = blockIdx.x;
+    const int64_t p0 = t * W;
+    const int64_t p1 = p0 + W < n_right ? p0 + W : n_right;
+    float m = 0.f;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) m = fmaxf(m, row_norm[perm ? perm[p] : p]);
+    __shared__ float part[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        if (threadIdx.x == 0) bound[t] = m;
     }
 }
 
@@ -114,17 +162,40 @@ int sg_feature_df(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const i
 }
 
 int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
-                  const float *val32, const int32_t *df_right, float right_norm, float budget, float threshold,
-                  float margin, float margin_per_feature, int32_t *out_indices, float *out_val32,
-                  int32_t *out_len, float *out_threshold, void *stream_) {
+                  const float *val32, const int32_t *df_right, const int8_t *prunable, float right_norm,
+                  float budget, float threshold, float margin, float margin_per_feature, int32_t *out_indices,
+                  float *out_val32, int32_t *out_len, float *out_threshold, float *out_pruned_norm,
+                  void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t n = row_end - row_begin;
     if (n <= 0) return SG_OK;
     if (!(budget >= 0.f) || !(right_norm >= 0.f)) return fail(SG_ERR_INVALID, "budget and right_norm must be >= 0");
     prune_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, val32, df_right,
-                                                              right_norm, budget, threshold, margin,
+                                                              prunable, right_norm, budget, threshold, margin,
                                                               margin_per_feature, out_indices, out_val32, out_len,
-                                                              out_threshold);
+                                                              out_threshold, out_pruned_norm);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+int sg_heavy_norms(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
+                   const float *val32, const int8_t *hrank, float *out_norm, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int64_t n = row_end - row_begin;
+    if (n <= 0) return SG_OK;
+    heavy_norms_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, val32, hrank,
+                                                               out_norm);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+int sg_tile_bounds(int64_t n_right, const int32_t *perm, const float *row_norm, int tile_w, float *bound,
+                   void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_right <= 0) return SG_OK;
+    if (tile_w <= 0) return fail(SG_ERR_INVALID, "tile_w must be positive");
+    const int64_t T = (n_right + tile_w - 1) / tile_w;
+    tile_bounds_kernel<<<(unsigned)T, 256, 0, st>>>(n_right, perm, row_norm, tile_w, bound);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }

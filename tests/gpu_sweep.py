@@ -9,7 +9,7 @@ from synth_corpus import make_names
 from string_grouper_b200 import _device as D, _ingest
 
 n = int(sys.argv[1])
-cfgs = [c.split(":") for c in sys.argv[2:]] or [["0.7", "f16", "0", "32"]]
+cfgs = [c.split(":") for c in sys.argv[2:]] or [["0.7", "u16", "0", "32"]]
 names = make_names(n, 0)
 data, offsets, flags, _ = _ingest.pack_strings([pd.Series(names)])
 A, _, _ = D.tfidf(data, offsets, n, 3, flags, np.float64)

@@ -61,7 +61,7 @@ def test_two_series_and_tilings_agree():
 
 @pytest.mark.parametrize("thr", [0.8, 0.5, 0.3])
 def test_pruning_and_accumulator_variants_agree(thr):
-    """Exact threshold pruning (csrc/sg_prune.cu) and the fp16 accumulator tile only change which candidates
+    """Exact threshold pruning (csrc/sg_prune.cu) and the fixed-point accumulator tile only change which candidates
     are generated, never the result: every variant returns the same triples, bit for bit, as the unpruned
     fp32 traversal, and those equal the oracle."""
     names = make_names(12000, seed=11)
@@ -71,8 +71,8 @@ def test_pruning_and_accumulator_variants_agree(thr):
     compare_triples(csr_triples(ref), base.host_triples(), len(names), thr, cutoff_row=cut, label="unpruned")
     b = base.host_triples()
     walked = {}
-    for prune, acc, tile_w in [(0.0, "f16", None), (0.5, "f32", None), (0.7, "f16", None), (0.9, "f32", 256),
-                               (0.95, "f16", 512), (0.7, "f16", 3072)]:
+    for prune, acc, tile_w in [(0.0, "u16", None), (0.5, "f32", None), (0.7, "u16", None), (0.9, "f32", 256),
+                               (0.95, "u16", 512), (0.7, "u16", 3072)]:
         st = {"count_macs": True}
         _, _, _, got = _run(names, None, 20, thr, prune=prune, acc=acc, tile_w=tile_w, stats=st)
         g = got.host_triples()
@@ -80,8 +80,8 @@ def test_pruning_and_accumulator_variants_agree(thr):
         for x, y in zip(b, g):
             assert np.array_equal(x, y), (prune, acc, tile_w)
         walked[(prune, acc)] = st.get("macs_walked")
-    full = walked[(0.0, "f16")]
-    assert walked[(0.7, "f16")] < 0.6 * full and walked[(0.95, "f16")] <= walked[(0.7, "f16")]
+    full = walked[(0.0, "u16")]
+    assert walked[(0.7, "u16")] < 0.6 * full and walked[(0.95, "u16")] <= walked[(0.7, "u16")]
 
 
 def test_pruning_two_series_unnormalised_rows():
