@@ -64,10 +64,9 @@ __global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr,
 // ---------------------------------------------------------------------------
 // candidate generation
 // ---------------------------------------------------------------------------
-constexpr int SHORT_BUCKET = 4;  // buckets up to this length are handled lane-privately
+constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
 
-// The kernel is latency-bound on L2 posting reads: 64 resident warps per SM (32 registers per thread)
-// beat deeper per-warp prefetching at 40-48 registers (measured, profiles/r1_notes.md).
+// The kernel is issue-bound: 64 resident warps per SM at 32 registers per thread (measured, profiles/r1_notes.md).
 constexpr int min_ctas(int nw) { return 64 / nw < 1 ? 1 : 64 / nw; }
 
 // Accumulator tile element.
@@ -128,30 +127,24 @@ struct AccOps<uint16_t> {
     }
 };
 
-// One bucket-directory batch of a row (32 features, one per lane) applied to the accumulator tile.
+// One bucket-directory batch of a row (32 features, one per lane: bucket [b0, b0+len) and left weight a)
+// applied to the accumulator tile.
+//   * buckets of LONG_BUCKET postings or more: the whole warp streams one bucket at a time;
+//   * all the others are walked as ONE concatenated list, 32 postings per step whatever the bucket boundaries
+//     (after pruning a row keeps its rarer features, whose buckets hold a dozen postings per tile: one bucket
+//     per step would leave most lanes idle).  Lane -> bucket by a 5-step binary search over the running
+//     sums; two lanes of a step may meet on one column, hence shared-memory atomics.
 template <typename AccT>
 __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint32_t *__restrict__ post, int b0,
                                               int len, float a, int lane,
                                               typename AccOps<AccT>::val_t &seen) {
     typedef AccOps<AccT> Ops;
-    const int b1 = b0 + len;
-    // short buckets: every lane walks its own bucket (one L2 latency for all of them);
-    // two lanes may meet on one column, hence the shared-memory atomic.
-    if (len > 0 && len <= SHORT_BUCKET) {
-        for (int j = 0; j < len; ++j) {
-            const uint32_t e = post[b0 + j];
-            seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e), a, post_w(e)));
-        }
-    }
-    __syncwarp();
-    // long buckets: the whole warp streams one bucket; columns inside one posting
-    // list are distinct, so the fp32 read-modify-write needs no atomics.
-    unsigned m = __ballot_sync(FULL, len > SHORT_BUCKET);
+    unsigned m = __ballot_sync(FULL, len >= LONG_BUCKET);
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const int s = __shfl_sync(FULL, b0, src);
-        const int e = __shfl_sync(FULL, b1, src);
+        const int e = s + __shfl_sync(FULL, len, src);
         const float ak = __shfl_sync(FULL, a, src);
         int p = s + lane;
         for (; p + 96 < e; p += 128) {
@@ -168,6 +161,31 @@ __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint
         }
         __syncwarp();
     }
+    // the concatenated walk over the remaining buckets
+    const int ln = len >= LONG_BUCKET ? 0 : len;
+    int incl = ln;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int d = b0 - (incl - ln);                    // posting index = d + position in the concatenated list
+    for (int item = lane; item - lane < total; item += 32) {
+        int k = 0;                                     // number of buckets that end at or before `item`
+#pragma unroll
+        for (int st = 16; st; st >>= 1) {
+            const int v = __shfl_sync(FULL, incl, k + st - 1);
+            if (v <= item) k += st;
+        }
+        const int dk = __shfl_sync(FULL, d, k);
+        const float ak = __shfl_sync(FULL, a, k);
+        if (item < total) {
+            const uint32_t e0 = post[dk + item];
+            seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e0), ak, post_w(e0)));
+        }
+    }
+    __syncwarp();
 }
 
 // Pruned left operand (sg_prune_rows; all three optional together): row i keeps only its first a_len[i] stored
@@ -218,8 +236,10 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         if (nf == 0) continue;
         const float thr_r = thr_row ? thr_row[row] : thr_all;
         const float xp = xp_norm ? xp_norm[row] : 0.f;
-        const int64_t t_begin = group * tiles_per_group;
-        const int64_t t_end = t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T;
+        // tile ids, directory slots (T * V1 < 2^31, checked by sg_postings_build) and positions fit 32 bits
+        const int t_begin = (int)(group * tiles_per_group);
+        const int t_end = (int)(t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T);
+        const int v1 = (int)V1;
 
         // the first 32 features of the row stay in registers; their directory entries for the next
         // column tile are fetched while the current tile is processed
@@ -230,17 +250,16 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
             a0 = Ops::left_weight(a_val[p0 + lane] * a_scale);
         }
         int2 d_next = make_int2(0, 0);
-        if (f0 >= 0) d_next = bdir[t_begin * V1 + f0];
+        if (f0 >= 0) d_next = bdir[t_begin * v1 + f0];
 
-        for (int64_t t = t_begin; t < t_end; ++t) {
-            const int64_t c0 = t * W;
+        for (int t = t_begin; t < t_end; ++t) {
             const int2 d0 = d_next;
-            if (f0 >= 0 && t + 1 < t_end) d_next = bdir[(t + 1) * V1 + f0];
+            if (f0 >= 0 && t + 1 < t_end) d_next = bdir[(t + 1) * v1 + f0];
             const val_t thr_c = Ops::threshold(xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r);
             val_t seen = 0;        // largest value this lane wrote into the tile
             apply_buckets<AccT>(acc, post, d0.x, d0.y, a0, lane, seen);
             if (nf > 32) {
-                const int2 *bd = bdir + t * V1;
+                const int2 *bd = bdir + t * v1;
                 for (int base = 32; base < nf; base += 32) {
                     const int k = base + lane;
                     int b0 = 0, len = 0;
@@ -284,9 +303,9 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                         const int i = __ffs(m) - 1;
                         m &= m - 1;
                         if (slot < cap) {
-                            const int64_t col = c0 + (int64_t)c * Ops::PER16 + i;
+                            const int col = t * W + c * Ops::PER16 + i;
                             cand_row[slot] = (int32_t)row;
-                            cand_col[slot] = perm_b ? perm_b[col] : (int32_t)col;
+                            cand_col[slot] = perm_b ? perm_b[col] : col;
                         }
                         ++slot;
                     }
