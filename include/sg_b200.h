@@ -199,12 +199,16 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len
  * and right row j in ascending feature order (the accumulation order of
  * sp_matmul_topn) in the matrix dtype (f64 default, sg.py:18), multiply and
  * add rounded separately (no FMA contraction) so that scores equal the CPU
- * path bit for bit.
+ * path bit for bit.  With `keep_count` == NULL score_out[i] is the score of candidate i.  Otherwise only the
+ * candidates scoring strictly above `keep_threshold` (sg.py:729/:740) are kept, compacted in no particular
+ * order into (keep_row, keep_col, score_out), and *keep_count [dev] (zeroed by the caller) receives their number.
  */
 int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
                const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
                const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
-               double *score_out /*[dev] n_cand*/, void *stream);
+               double *score_out /*[dev] n_cand*/, double keep_threshold, int32_t *keep_row /*[dev] n_cand or NULL*/,
+               int32_t *keep_col /*[dev] n_cand or NULL*/, unsigned long long *keep_count /*[dev] 1 or NULL*/,
+               void *stream);
 
 /*
  * Per-row selection: keep score > threshold (strict, sg.py:729/:740), at most

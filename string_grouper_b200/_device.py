@@ -16,14 +16,16 @@ _TORCH = None
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0, "order": 0, "tiles": 0, "groups": 0, "gather": 0, "prune": 0}
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 112 KB of accumulators per CTA, two CTAs per SM
-DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "32"))
+TRANSFER_BYTES = {"d2h": 0, "h2d": 0}      # bytes moved by the bulk copies (bench.py e2e accounting)
+
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 72 KB of accumulators per CTA, three CTAs per SM
+DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "16"))          # 16 warps x 3 CTAs at 40 registers (no spills)
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
 U16_MARGIN_PER_FEATURE = 2e-5   # 1/32768 fixed-point accumulator tile: one rounding of <= 2^-16 per added product
 # Exact threshold pruning (csrc/sg_prune.cu): the most expensive heavy features of a left row are skipped while
 # their norm times the largest right-row norm stays below PRUNE_FRAC * min_similarity.  0 switches it off.
-PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.7"))
+PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.9"))
 ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulator tile: u16 | f32
 
 
@@ -54,6 +56,24 @@ def _stream():
 
 def _empty(n, dtype, device):
     return torch().empty(max(int(n), 1), dtype=dtype, device=device)
+
+
+def to_host(*tensors):
+    """Device tensors -> numpy arrays through page-locked staging buffers (torch's caching host allocator
+    re-uses them from call to call): all copies are queued on the current stream, one synchronisation.
+    Pageable `.cpu()` copies run at a fraction of the PCIe rate and were the largest end-to-end cost."""
+    t = torch()
+    tensors = [x.contiguous() for x in tensors]
+    TRANSFER_BYTES["d2h"] += sum(x.numel() * x.element_size() for x in tensors)
+    try:
+        outs = [t.empty(x.shape, dtype=x.dtype, pin_memory=bool(x.numel())) for x in tensors]
+    except RuntimeError:          # page-locking refused (memlock limit): plain copies
+        return [x.cpu().numpy() for x in tensors]
+    for h, x in zip(outs, tensors):
+        if x.numel():
+            h.copy_(x, non_blocking=True)
+    t.cuda.current_stream().synchronize()
+    return [h.numpy() for h in outs]
 
 
 class DeviceCSR:
@@ -236,8 +256,11 @@ class DeviceMatches:
         return self
 
     def host_triples(self):
+        """(row int64, col int64, score f64) on the host; the widening to the reference's int64 columns
+        (string_grouper.py:759-763) happens on the device."""
         n = self.nnz
-        return (self.d_row[:n].cpu().numpy(), self.d_col[:n].cpu().numpy(), self.d_score[:n].cpu().numpy())
+        t = torch()
+        return tuple(to_host(self.d_row[:n].to(t.int64), self.d_col[:n].to(t.int64), self.d_score[:n]))
 
     def to_scipy(self):
         if self._host is None:
@@ -263,9 +286,10 @@ class DeviceMatches:
 
 
 def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
-    """Column-tile width and warps per CTA.  Default: warps * tile_w * acc_bytes = 112 KB, two CTAs per SM."""
+    """Column-tile width and warps per CTA.  Default: warps * tile_w * acc_bytes = 72 KB with 16 warps (three CTAs
+    per SM), 112 KB otherwise (two CTAs of 32 warps)."""
     warps = int(warps or DEFAULT_WARPS)
-    tile_w = int(tile_w or DEFAULT_TILE_W) or (112 << 10) // (warps * acc_bytes)
+    tile_w = int(tile_w or DEFAULT_TILE_W) or ((72 << 10) if warps == 16 else (112 << 10)) // (warps * acc_bytes)
     q = 512 // acc_bytes                               # tile bytes must be a multiple of 512
     need = ((max(int(n_right), 1) + q - 1) // q) * q
     tile_w = max(q, min(tile_w, 65536) // q * q)
@@ -423,11 +447,19 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
         stats["tiles_per_group"] = tiles_per_group
 
+    # exact scores; only the candidates strictly above the threshold go on to the selection sorts
     score = _empty(n_cand, t.float64, dev)
+    keep_row = _empty(n_cand, t.int32, dev)
+    keep_col = _empty(n_cand, t.int32, dev)
+    counters.zero_()
     _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
                             _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
-                            _stream()))
+                            float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _stream()))
     LAUNCH_COUNTS["rescore"] += 1
+    n_cand = int(counters[0].item())
+    cand_row, cand_col = keep_row, keep_col
+    if stats is not None:
+        stats["n_above_threshold"] = n_cand
 
     out_indptr = _empty(n_rows + 1, t.int64, dev)
     out_row = _empty(n_cand, t.int32, dev)
@@ -491,24 +523,33 @@ class RawStrings:
         self.d_bytes, self.d_off, self.n_master, self.n_docs = d_bytes, d_off, int(n_master), int(n_docs)
 
 
-def gather_strings(raw, doc_base, positions, n_sel):
-    """(offsets int64 [n_sel+1], bytes uint8) on the host of the strings at `positions` (device int32) of the Series
-    starting at document `doc_base`: the `Series.iloc[...]` of get_matches (string_grouper.py:462, :467)."""
+def gather_strings(raw, sides):
+    """For every (doc_base, positions, n_sel) in `sides`: (offsets int64 [n_sel+1], bytes uint8) on the host of the
+    strings at `positions` (device int32) of the Series starting at document `doc_base` — the
+    `Series.iloc[...]` of get_matches (string_grouper.py:462, :467).  Two synchronisations in total: the byte
+    counts, then all offsets and bytes."""
     t = require_cuda()
     L = _lib.load()
     dev = raw.d_off.device
-    out_off = _empty(n_sel + 1, t.int64, dev)
-    ws_bytes = int(L.sg_gather_workspace_bytes(n_sel))
-    ws = _empty(ws_bytes, t.uint8, dev)
-    _lib.check(L.sg_gather_offsets(_ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions), _ptr(out_off), _ptr(ws),
-                                   ws_bytes, _stream()))
-    off_host = out_off[:n_sel + 1].cpu().numpy()
-    total = int(off_host[-1])
-    out = _empty(total, t.uint8, dev)
-    _lib.check(L.sg_gather_bytes(_ptr(raw.d_bytes), _ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions),
-                                 _ptr(out_off), _ptr(out), _stream()))
-    LAUNCH_COUNTS["gather"] += 2
-    return off_host, out[:total].cpu().numpy()
+    offs = []
+    for doc_base, positions, n_sel in sides:
+        out_off = _empty(n_sel + 1, t.int64, dev)
+        ws_bytes = int(L.sg_gather_workspace_bytes(n_sel))
+        ws = _empty(ws_bytes, t.uint8, dev)
+        _lib.check(L.sg_gather_offsets(_ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions), _ptr(out_off),
+                                       _ptr(ws), ws_bytes, _stream()))
+        offs.append(out_off)
+    totals = t.stack([o[n_sel] for o, (_, _, n_sel) in zip(offs, sides)]).cpu().numpy()
+    datas = []
+    for out_off, total, (doc_base, positions, n_sel) in zip(offs, totals, sides):
+        out = _empty(int(total), t.uint8, dev)
+        _lib.check(L.sg_gather_bytes(_ptr(raw.d_bytes), _ptr(raw.d_off), int(doc_base), n_sel, _ptr(positions),
+                                     _ptr(out_off), _ptr(out), _stream()))
+        LAUNCH_COUNTS["gather"] += 2
+        datas.append(out[:int(total)])
+    host = to_host(*([o[:n_sel + 1] for o, (_, _, n_sel) in zip(offs, sides)] + datas))
+    k = len(sides)
+    return [(host[i], host[k + i]) for i in range(k)]
 
 
 def matches_from_scipy(m):
@@ -574,6 +615,7 @@ def upload_strings(data, offsets, device=None):
 def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None, df_allreduce=None, n_docs_fit=None):
     """K1 from host buffers: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM."""
     d_bytes, d_off, total = upload_strings(data, offsets, device)
+    TRANSFER_BYTES["h2d"] += int(total + 8 * len(offsets))
     if stats is not None:
         stats["h2d_bytes"] = int(total + 8 * len(offsets))
         stats["raw"] = RawStrings(d_bytes, d_off, n_master, len(offsets) - 1)

@@ -66,8 +66,10 @@ __global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr,
 // ---------------------------------------------------------------------------
 constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
 
-// The kernel is issue-bound: 64 resident warps per SM at 32 registers per thread (measured, profiles/r1_notes.md).
-constexpr int min_ctas(int nw) { return 64 / nw < 1 ? 1 : 64 / nw; }
+// Resident CTAs per SM the register allocation is made for: 2 x 32 warps at 32 registers per thread, or
+// 3 x 16 warps at 40 registers (no spills in the tile loop; the kernel is bound by the shared-memory pipe,
+// 48 warps hide the L2 latency of the posting reads as well as 64).
+constexpr int min_ctas(int nw) { return nw == 16 ? 3 : (64 / nw < 1 ? 1 : 64 / nw); }
 
 // Accumulator tile element.
 //   float    : fp32 scores, read-modify-write in the long-bucket path, CAS-loop atomics in the short one.
@@ -358,17 +360,42 @@ __device__ __forceinline__ T merge_dot(const int32_t *__restrict__ ai, const T *
     return sum;
 }
 
+// `keep_count` == NULL: out[i] = exact score of candidate i.  Otherwise only the candidates whose exact score
+// exceeds `keep_thr` (strict, string_grouper.py:729/:740) survive, appended in no particular order to
+// (keep_row, keep_col, out) through one warp-aggregated atomic per warp: the selection sorts that follow then
+// work on the matches-to-be instead of on every candidate the pruned traversal had to report.
 template <typename T>
 __global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
                                const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                                const T *__restrict__ a_val, const int64_t *__restrict__ b_indptr,
                                const int32_t *__restrict__ b_idx, const T *__restrict__ b_val,
-                               double *__restrict__ out) {
+                               double *__restrict__ out, double keep_thr, int32_t *__restrict__ keep_row,
+                               int32_t *__restrict__ keep_col, unsigned long long *__restrict__ keep_count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t r = cr[i], c = cc[i];
-    out[i] = (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+    int32_t r = 0, c = 0;
+    double sc = 0.0;
+    bool keep = false;
+    if (i < n) {
+        r = cr[i];
+        c = cc[i];
+        sc = (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
                                   b_indptr[c + 1]);
+        if (!keep_count) out[i] = sc;
+        keep = keep_count && sc > keep_thr;
+    }
+    if (!keep_count) return;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(keep_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (keep) {
+        const unsigned long long w = base + __popc(m & ((1u << lane) - 1u));
+        keep_row[w] = r;
+        keep_col[w] = c;
+        out[w] = sc;
+    }
 }
 
 template <typename T>
@@ -632,18 +659,22 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
 
 int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const int64_t *a_indptr,
                const int32_t *a_indices, const void *a_val, const int64_t *b_indptr, const int32_t *b_indices,
-               const void *b_val, int dtype, double *score_out, void *stream_) {
+               const void *b_val, int dtype, double *score_out, double keep_threshold, int32_t *keep_row,
+               int32_t *keep_col, unsigned long long *keep_count, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_cand <= 0) return SG_OK;
+    if (keep_count && (!keep_row || !keep_col)) return fail(SG_ERR_INVALID, "keep_count needs keep_row and keep_col");
     const unsigned grid = (unsigned)((n_cand + 255) / 256);
     if (dtype == SG_DTYPE_F64)
         rescore_kernel<double><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
                                                      (const double *)a_val, b_indptr, b_indices,
-                                                     (const double *)b_val, score_out);
+                                                     (const double *)b_val, score_out, keep_threshold, keep_row,
+                                                     keep_col, keep_count);
     else if (dtype == SG_DTYPE_F32)
         rescore_kernel<float><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
                                                     (const float *)a_val, b_indptr, b_indices,
-                                                    (const float *)b_val, score_out);
+                                                    (const float *)b_val, score_out, keep_threshold, keep_row,
+                                                    keep_col, keep_count);
     else
         return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
     SG_LAUNCH_CHECK();

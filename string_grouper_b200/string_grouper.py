@@ -345,8 +345,8 @@ class StringGrouper(object):
             m = matches.tocsr()
             r, c = m.nonzero()
             s = m.data
-        return pd.DataFrame({'master_side': np.asarray(r).astype(np.int64),
-                             'dupe_side': np.asarray(c).astype(np.int64),
+        return pd.DataFrame({'master_side': np.asarray(r).astype(np.int64, copy=False),
+                             'dupe_side': np.asarray(c).astype(np.int64, copy=False),
                              'similarity': np.asarray(s)}, copy=False)
 
     @staticmethod
@@ -384,9 +384,10 @@ class StringGrouper(object):
                 and _is_arrow_str(self._master) and _is_arrow_str(right_strings)
                 and raw.n_master == len(self._master)):
             # strings and match positions are both in HBM: gather there, wrap the result as Arrow arrays
-            lvals = _gathered_array(self._master, *_device.gather_strings(raw, 0, dev.d_row, dev.nnz))
             rbase = 0 if self._duplicates is None else raw.n_master
-            rvals = _gathered_array(right_strings, *_device.gather_strings(raw, rbase, dev.d_col, dev.nnz))
+            lhost, rhost = _device.gather_strings(raw, [(0, dev.d_row, dev.nnz), (rbase, dev.d_col, dev.nnz)])
+            lvals = _gathered_array(self._master, *lhost)
+            rvals = _gathered_array(right_strings, *rhost)
         left = _take_side(self._master, lpos, DEFAULT_COLUMN_NAME, ignore_index, LEFT_PREFIX, mirror=False,
                           values=lvals)
         right = _take_side(right_strings, rpos, DEFAULT_COLUMN_NAME, ignore_index, RIGHT_PREFIX, mirror=True,
