@@ -361,11 +361,28 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and world == 1:      # the ncu capture is a 1-GPU launch over all rows
         traffic = json.load(open(tpath)).get("%d" % n)
+    # what the pruned traversal really walks (one extra, untimed launch with the counting switched on)
+    st_count = {"count_macs": True}
+    D.cossim_topn(A, A, TOP_N, MIN_SIM, row_begin=lo, row_end=hi, stats=st_count)
+    walked = st_count.get("macs_walked")
+    pipe = None
+    ppath = os.path.join(ROOT, "profiles", "pipe.json")
+    if os.path.exists(ppath) and world == 1:
+        pipe = json.load(open(ppath)).get("%d" % n)
     roofline = {"bound": "hbm", "kernel": "sg::cossim_candidates_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "macs_per_launch": macs_local, "macs_total": macs_total,
                 "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms / float(np.mean(step_ms)),
-                "tile": {k: info["stats"].get(k) for k in ("tile_w", "warps", "n_tiles", "n_candidates")}}
+                "note": "achieved/frac follow SURVEY.md §8d: bytes of the FULL Gustavson traversal / kernel time; "
+                        "exact threshold pruning walks only `walked.macs` postings (4 B each, L2-resident), so frac > 1 "
+                        "is an algorithmic gain, not HBM utilisation; the measured limiter is in `pipe` (ncu)",
+                "walked": {"macs": walked, "share_of_full": (walked / macs_local) if walked else None,
+                           "posting_bytes": 4 * walked if walked else None,
+                           "posting_GBps": (4 * walked / (k2_ms / 1e3) / 1e9) if walked else None,
+                           "prune": st_count.get("prune"), "accumulator": st_count.get("acc")},
+                "pipe": pipe,
+                "tile": {k: info["stats"].get(k) for k in ("tile_w", "warps", "n_tiles", "n_candidates",
+                                                            "n_above_threshold")}}
 
     if rank != 0:
         if world > 1:

@@ -77,7 +77,7 @@ def main():
 
     # K2 kernel timing + MACs on this rank (one extra product with event timing)
     A, B = sg._get_tf_idf_matrices()
-    stats = {"time_kernels": True}
+    stats = {"time_kernels": True, "count_macs": True}
     lo, hi = (0, A.shape[0])
     if world > 1 and getattr(A, "row_offset", None) is None:
         from string_grouper_b200 import _dist
@@ -97,7 +97,10 @@ def main():
             "matches": int(len(sg._matches_list)), "k2_macs_rank0": macs, "k2_kernel_ms_rank0": k_ms,
             "k2_algorithmic_GBps_rank0": 8 * macs / (k_ms / 1e3) / 1e9,
             "k2_frac_of_6570": 8 * macs / (k_ms / 1e3) / 1e9 / 6570.0,
-            "n_candidates_rank0": stats.get("n_candidates")}), flush=True)
+            "k2_walked_macs_rank0": stats.get("macs_walked"), "prune": stats.get("prune"),
+            "accumulator": stats.get("acc"), "tile_w": stats.get("tile_w"), "warps": stats.get("warps"),
+            "n_candidates_rank0": stats.get("n_candidates"),
+            "n_above_threshold_rank0": stats.get("n_above_threshold")}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -27,6 +27,8 @@ U16_MARGIN_PER_FEATURE = 2e-5   # 1/32768 fixed-point accumulator tile: one roun
 # their norm times the largest right-row norm stays below PRUNE_FRAC * min_similarity.  0 switches it off.
 PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.9"))
 ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulator tile: u16 | f32
+MAX_CAND_DENSITY = float(os.environ.get("SG_B200_MAX_CAND_DENSITY", "1.5e-3"))   # candidates per (row, column) pair
+CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
 
 
 def torch():
@@ -366,6 +368,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         acc = "f32"      # also near-zero thresholds: a tiny positive score must not round to a fixed-point zero
     acc_code = _lib.SG_ACC_U16 if acc == "u16" else _lib.SG_ACC_F32
     margin_pf = U16_MARGIN_PER_FEATURE if acc == "u16" else 0.0
+    prune_auto = prune is None          # the caller left the level open: it may be lowered, see below
     prune = PRUNE_FRAC if prune is None else float(prune)
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
@@ -383,15 +386,49 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
-    # exact threshold pruning of the left rows; the fixed-point tile always takes per-row thresholds (its
-    # margin grows with the number of features added)
-    if (prune > 0.0 and thr_c > 0.0) or margin_pf > 0.0:
-        l_idx, l_val, l_len, l_thr, l_xp = prune_left(A, B, hrank, row_begin, row_end, float(threshold), margin,
-                                                      margin_pf, prune if thr_c > 0.0 else 0.0)
-    else:
-        l_idx, l_val, l_len, l_thr, l_xp = A.d_indices, A.d_val32, None, None, None
+    dummy = _empty(1, t.int32, dev)
+    pruned = {}
+
+    def launch(perm, rb, re_, row_buf, col_buf, capacity):
+        l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+        counters.zero_()
+        _lib.check(L.sg_cossim_candidates(
+            _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
+            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, acc_code, max(B.norm_bound, 1.0),
+            thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity,
+            c_count, c_queue, warps, _stream()))
+        LAUNCH_COUNTS["candidates"] += 1
+
+    # Exact threshold pruning of the left rows (the fixed-point tile always takes per-row thresholds: its margin
+    # grows with the number of features added).  A counting pass over a sample of the rows (in processing order,
+    # so clusters of identical names are sampled in proportion) sizes the candidate buffers; when the caller left
+    # the pruning level open and the sample reports more than MAX_CAND_DENSITY candidates per (row, column) pair,
+    # the level is lowered: every candidate costs an exact re-score, every skipped posting saves one update.
+    levels = [prune]
+    if prune_auto and prune > 0.0 and thr_c > 0.0:
+        levels = [prune, 0.75 * prune, 0.5 * prune, 0.25 * prune, 0.0]
+    sample = None
+    if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:
+        stride = max(64, n_rows // 8192)
+        sample = perm_a[:n_rows:stride].contiguous()
+    est = None
+    for level in levels:
+        if (level > 0.0 and thr_c > 0.0) or margin_pf > 0.0:
+            pruned["arrays"] = prune_left(A, B, hrank, row_begin, row_end, float(threshold), margin, margin_pf,
+                                          level if thr_c > 0.0 else 0.0)
+        else:
+            pruned["arrays"] = (A.d_indices, A.d_val32, None, None, None)
+        prune = level
+        if sample is None:
+            break
+        launch(sample, row_begin, row_begin + int(sample.numel()), dummy, dummy, 0)
+        est = int(counters[0].item()) * stride
+        if est <= MAX_CAND_DENSITY * n_rows * n_right:
+            break
+    l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
     if stats is not None:
         stats["prune"], stats["acc"] = prune, acc
+        stats["n_candidates_estimate"] = est
         if stats.get("count_macs") and l_len is not None:
             df = feature_df(B).long()
             pos = t.arange(A.d_indices.numel(), device=dev)
@@ -402,64 +439,65 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             stats["macs_walked"] = int(df[l_idx.long().clamp(0, A.shape[1] - 1)][live].sum().item())
             stats["features_kept"] = int(live.sum().item())
 
-    def launch(perm, n_perm_rows, rb, re_, row_buf, col_buf, capacity):
+    # Left rows are taken in chunks (slices of the processing order) whose candidates fit CAND_CHUNK entries;
+    # every chunk is re-scored exactly right away and only the pairs strictly above the threshold are kept.
+    n_chunks = 1 if est is None else max(1, -(-int(1.3 * est) // CAND_CHUNK))
+    rows_per_chunk = -(-n_rows // n_chunks)
+    kept = []
+    n_cand_total = 0
+    for lo in range(0, n_rows, rows_per_chunk):
+        hi = min(lo + rows_per_chunk, n_rows)
+        perm_chunk = perm_a if (lo == 0 and hi == n_rows) else perm_a[lo:hi]
+        if est is not None:
+            cap = min(max(int(1.3 * est * (hi - lo) / n_rows) + (1 << 22), 1 << 22), 1 << 31)
+        for attempt in range(3):
+            cand_row = _empty(cap, t.int32, dev)
+            cand_col = _empty(cap, t.int32, dev)
+            if stats is not None and stats.get("time_kernels"):
+                ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                ev0.record()
+            launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap)
+            if stats is not None and stats.get("time_kernels"):
+                ev1.record()
+                stats.setdefault("candidate_events", []).append((ev0, ev1))
+            n_cand = int(counters[0].item())
+            if n_cand <= cap:
+                break
+            if n_cand * 24 > 96 * 2**30:
+                raise OverflowError("%d candidate pairs above the threshold do not fit the candidate buffer; "
+                                    "raise min_similarity or split the input" % n_cand)
+            cap = n_cand
+        else:
+            raise OverflowError("candidate buffer overflow")
+        n_cand_total += n_cand
+        # exact scores; only the candidates strictly above the threshold go on to the selection sorts
+        score = _empty(n_cand, t.float64, dev)
+        keep_row = _empty(n_cand, t.int32, dev)
+        keep_col = _empty(n_cand, t.int32, dev)
         counters.zero_()
-        _lib.check(L.sg_cossim_candidates(
-            _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
-            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, acc_code, max(B.norm_bound, 1.0),
-            thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity,
-            c_count, c_queue, warps, _stream()))
-        LAUNCH_COUNTS["candidates"] += 1
-
-    if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:
-        # Size the candidate buffer from a counting pass over every 64th row (in signature order, so clusters of
-        # identical names are sampled in proportion): duplicate clusters make the count vary from 10 to 200 per row
-        # between corpora, and an undersized buffer would cost a second full launch.
-        stride = 64
-        sample = perm_a[:n_rows:stride].contiguous()
-        dummy = _empty(1, t.int32, dev)
-        launch(sample, int(sample.numel()), row_begin, row_begin + int(sample.numel()), dummy, dummy, 0)
-        est = int(counters[0].item()) * stride
-        cap = min(max(int(1.3 * est) + (1 << 22), 1 << 22), 1 << 31)
-        if stats is not None:
-            stats["n_candidates_estimate"] = est
-    for attempt in range(3):
-        cand_row = _empty(cap, t.int32, dev)
-        cand_col = _empty(cap, t.int32, dev)
-        if stats is not None and stats.get("time_kernels"):
-            ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-            ev0.record()
-        launch(perm_a, n_rows, row_begin, row_end, cand_row, cand_col, cap)
-        if stats is not None and stats.get("time_kernels"):
-            ev1.record()
-            stats.setdefault("candidate_events", []).append((ev0, ev1))
-        n_cand = int(counters[0].item())
-        if n_cand <= cap:
-            break
-        if n_cand * 24 > 64 * 2**30:
-            raise OverflowError("%d candidate pairs above the threshold do not fit the candidate buffer; "
-                                "raise min_similarity or split the input" % n_cand)
-        cap = n_cand
+        _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
+                                _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
+                                float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _stream()))
+        LAUNCH_COUNTS["rescore"] += 1
+        n_keep = int(counters[0].item())
+        if n_chunks > 1:      # release the chunk-sized buffers, keep the survivors
+            keep_row, keep_col, score = keep_row[:n_keep].clone(), keep_col[:n_keep].clone(), score[:n_keep].clone()
+        kept.append((keep_row, keep_col, score, n_keep))
+        del cand_row, cand_col
+    if len(kept) == 1:
+        cand_row, cand_col, score, n_cand = kept[0]
     else:
-        raise OverflowError("candidate buffer overflow")
+        n_cand = sum(k[3] for k in kept)
+        cand_row = t.cat([k[0][:k[3]] for k in kept]) if n_cand else _empty(1, t.int32, dev)
+        cand_col = t.cat([k[1][:k[3]] for k in kept]) if n_cand else _empty(1, t.int32, dev)
+        score = t.cat([k[2][:k[3]] for k in kept]) if n_cand else _empty(1, t.float64, dev)
+    del kept
     if stats is not None:
-        stats["n_candidates"] = n_cand
+        stats["n_candidates"] = n_cand_total
+        stats["n_above_threshold"] = n_cand
+        stats["n_row_chunks"] = n_chunks
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
         stats["tiles_per_group"] = tiles_per_group
-
-    # exact scores; only the candidates strictly above the threshold go on to the selection sorts
-    score = _empty(n_cand, t.float64, dev)
-    keep_row = _empty(n_cand, t.int32, dev)
-    keep_col = _empty(n_cand, t.int32, dev)
-    counters.zero_()
-    _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
-                            _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
-                            float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _stream()))
-    LAUNCH_COUNTS["rescore"] += 1
-    n_cand = int(counters[0].item())
-    cand_row, cand_col = keep_row, keep_col
-    if stats is not None:
-        stats["n_above_threshold"] = n_cand
 
     out_indptr = _empty(n_rows + 1, t.int64, dev)
     out_row = _empty(n_cand, t.int32, dev)

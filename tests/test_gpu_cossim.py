@@ -106,6 +106,30 @@ def test_pruning_two_series_unnormalised_rows():
         compare_triples(csr_triples(ref), got.host_triples(), len(dupes), 0.6, cutoff_row=cut, label="unnormalised")
 
 
+def test_row_chunks_and_adaptive_pruning_level(monkeypatch):
+    """Left rows are processed in chunks when the candidate estimate exceeds CAND_CHUNK, and the pruning level is
+    lowered when the sample pass reports too many candidates per pair; neither changes the result."""
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    names = make_names(70000, seed=13)
+    m, _, _ = P.tf_idf_matrices(names)
+    A = D.DeviceCSR.from_scipy(m)
+    base = D.cossim_topn(A, A, 20, 0.8, prune=0.0, acc="f32")
+    b = base.host_triples()
+    st = {}
+    monkeypatch.setattr(D, "CAND_CHUNK", 1 << 19)
+    got = D.cossim_topn(A, A, 20, 0.8, stats=st)
+    assert st["n_row_chunks"] > 1
+    for x, y in zip(b, got.host_triples()):
+        assert np.array_equal(x, y)
+    st2 = {}
+    monkeypatch.setattr(D, "MAX_CAND_DENSITY", 1e-7)
+    got2 = D.cossim_topn(A, A, 20, 0.8, stats=st2)
+    assert st2["prune"] < st["prune"]
+    for x, y in zip(b, got2.host_triples()):
+        assert np.array_equal(x, y)
+
+
 def test_long_rows():
     """strings of several hundred characters (more than 32 features per row: several lane batches)."""
     from string_grouper_b200 import _device as D
