@@ -388,19 +388,24 @@ class StringGrouper(object):
             lhost, rhost = _device.gather_strings(raw, [(0, dev.d_row, dev.nnz), (rbase, dev.d_col, dev.nnz)])
             lvals = _gathered_array(self._master, *lhost)
             rvals = _gathered_array(right_strings, *rhost)
-        left = _take_side(self._master, lpos, DEFAULT_COLUMN_NAME, ignore_index, LEFT_PREFIX, mirror=False,
-                          values=lvals)
-        right = _take_side(right_strings, rpos, DEFAULT_COLUMN_NAME, ignore_index, RIGHT_PREFIX, mirror=True,
-                           values=rvals)
-        similarity = pairs.similarity.reset_index(drop=True)
-        if self._master_id is None:
-            parts = [left, similarity, right]
-        else:
+        sides = [(self._master, lpos, DEFAULT_COLUMN_NAME, ignore_index, LEFT_PREFIX, False, lvals),
+                 (right_strings, rpos, DEFAULT_COLUMN_NAME, ignore_index, RIGHT_PREFIX, True, rvals)]
+        if self._master_id is not None:
             right_ids = self._master_id if self._duplicates is None else self._duplicates_id
-            left_id = _take_side(self._master_id, lpos, DEFAULT_ID_NAME, True, LEFT_PREFIX, mirror=False)
-            right_id = _take_side(right_ids, rpos, DEFAULT_ID_NAME, True, RIGHT_PREFIX, mirror=True)
-            parts = [left, left_id, similarity, right_id, right]
-        return pd.concat(parts, axis=1)
+            sides.insert(1, (self._master_id, lpos, DEFAULT_ID_NAME, True, LEFT_PREFIX, False, None))
+            sides.insert(2, (right_ids, rpos, DEFAULT_ID_NAME, True, RIGHT_PREFIX, True, None))
+        # fast path (millions of matches): every side reduces to plain columns -> ONE DataFrame construction
+        cols = [_side_columns(*sd) for sd in sides]
+        if all(c is not None for c in cols):
+            half = len(cols) // 2
+            flat = [kv for c in cols[:half] for kv in c] + [('similarity', pairs.similarity.to_numpy())] + \
+                   [kv for c in cols[half:] for kv in c]
+            if len({k for k, _ in flat}) == len(flat):
+                return pd.DataFrame(dict(flat), copy=False)
+        frames = [_take_side(*sd[:6], values=sd[6]) for sd in sides]
+        similarity = pairs.similarity.reset_index(drop=True)
+        half = len(frames) // 2
+        return pd.concat(frames[:half] + [similarity] + frames[half:], axis=1)
 
     @validate_is_fit
     def get_groups(self, ignore_index: Optional[bool] = None,
@@ -629,6 +634,26 @@ def _gathered_array(series, offsets, data):
     n = len(offsets) - 1
     arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
     return type(series.array)(pa.chunked_array([arr]), dtype=series.dtype)
+
+
+def _side_columns(series, positions, default_name, drop_index, prefix, mirror, values=None):
+    """[(column label, values)] of one side of get_matches when it reduces to plain columns (index dropped, or an
+    unnamed single-level index), else None.  Same labels / order as _take_side."""
+    name = series.name if series.name else default_name
+    index = series.index
+    if not (drop_index or (index.nlevels == 1 and index.name is None and name != 'index')):
+        return None
+    taken = series.array.take(positions) if values is None else values
+    out = [(f"{prefix}{name}", taken)]
+    if drop_index:
+        return out
+    if isinstance(index, pd.RangeIndex):
+        pos64 = np.asarray(positions, dtype=np.int64)
+        labels = pos64 if (index.start == 0 and index.step == 1) else index.start + index.step * pos64
+    else:
+        labels = index.to_numpy()[positions]
+    level = (f"{prefix}index", labels)
+    return out + [level] if mirror else [level] + out
 
 
 def _take_side(series, positions, default_name, drop_index, prefix, mirror, values=None):
