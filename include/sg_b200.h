@@ -112,11 +112,13 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w);
  * Right matrix -> tile-major, column-sorted postings (the transpose that sp_matmul_topn performs on
  * `Bi.T`, sg.py:727/:738, done once and laid out for the kernel).  The right rows are taken in the
  * order `rank` (position of every row in heavy-feature signature order, sg_row_order; NULL = input
- * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (t, f) = the docs of feature f
- * inside tile t, sorted by position, at bucket_ptr[t*(n_cols+1)+f]; a posting is 4 bytes:
+ * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (f, t) = the docs of feature f
+ * inside tile t, sorted by position, at bucket_ptr[f*T + t] (feature-major, T = sg_num_tiles); a posting is 4 bytes:
  * position - t*tile_w in the low 16 bits, the weight rounded to fp16 in the high 16 bits (candidate
  * scores only need to be within the caller's margin; every candidate is re-scored exactly).  `bucket_dir` (optional) receives the same directory as aligned
- * {int32 start, int32 length} pairs, T*(n_cols+1) of them, the form sg_cossim_candidates reads.
+ * 8-byte entries {int32 start, u16 length, fp16 largest |weight| of the bucket}, T*(n_cols+1) of them, the form
+ * sg_cossim_candidates reads: the largest weights let it skip every (left row, column tile) pair whose score
+ * bound sum_f |a_f| * max|w_(f,t)| cannot reach the candidate threshold.  tile_w <= 32768.
  * `indptr` may be a row-range view (indptr_base = indptr[0]).
  */
 size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);

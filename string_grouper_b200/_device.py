@@ -294,7 +294,7 @@ def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
     tile_w = int(tile_w or DEFAULT_TILE_W) or ((72 << 10) if warps == 16 else (112 << 10)) // (warps * acc_bytes)
     q = 512 // acc_bytes                               # tile bytes must be a multiple of 512
     need = ((max(int(n_right), 1) + q - 1) // q) * q
-    tile_w = max(q, min(tile_w, 65536) // q * q)
+    tile_w = max(q, min(tile_w, 32768) // q * q)
     return min(tile_w, need), warps
 
 

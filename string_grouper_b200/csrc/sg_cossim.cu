@@ -20,12 +20,13 @@ namespace sg {
 // ---------------------------------------------------------------------------
 // postings build: tile-major, column-sorted, in signature order of the right rows
 // ---------------------------------------------------------------------------
-// key = (bucket << 16) | local column, bucket = t * (n_cols + 1) + f, t = rank[doc] / tile_w
+// key = (bucket << 16) | local column; bucket = f * T + t (feature-major: the buckets a left row walks for one of its
+// features over consecutive column tiles are neighbours in the directory and in the posting array), t = rank[doc] / tile_w
 __global__ void postings_keys_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
                                      const int32_t *__restrict__ indices, const float *__restrict__ val,
-                                     const int32_t *__restrict__ rank, int W, int64_t V1, int64_t base,
+                                     const int32_t *__restrict__ rank, int W, int64_t T, int64_t base, float w_scale,
                                      uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                     int32_t *__restrict__ cnt) {
+                                     int32_t *__restrict__ cnt, uint32_t *__restrict__ maxw) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int64_t pos = rank ? rank[row] : row;
@@ -33,10 +34,13 @@ __global__ void postings_keys_kernel(int64_t n_rows, const int64_t *__restrict__
     const uint64_t local = (uint64_t)(pos - t * W);
     const int64_t p1 = indptr[row + 1];
     for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32) {
-        const int64_t b = t * V1 + indices[p];
+        const int64_t b = (int64_t)indices[p] * T + t;
+        const float w = val[p] * w_scale;
         keys[p - base] = ((uint64_t)b << 16) | local;
-        vals[p - base] = __float_as_uint(val[p]);
+        vals[p - base] = __float_as_uint(w);
         atomicAdd(cnt + b, 1);
+        // largest |weight| of the bucket as the fp16 value the kernel will see (non-negative halves order like integers)
+        atomicMax(maxw + b, (uint32_t)__half_as_ushort(__float2half_rn(fabsf(w))));
     }
 }
 
@@ -44,10 +48,10 @@ __global__ void postings_keys_kernel(int64_t n_rows, const int64_t *__restrict__
 // candidate scores only have to be within CAND_MARGIN of the exact ones (every candidate is re-scored in the
 // matrix dtype): an fp16 weight is off by at most 2^-11 relative, so a score by at most 4.9e-4.
 __global__ void postings_pack_kernel(int64_t nnz, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     float w_scale, uint32_t *__restrict__ post) {
+                                     uint32_t *__restrict__ post) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) {
-        const unsigned h = __half_as_ushort(__float2half_rn(__uint_as_float(vals[i]) * w_scale));
+        const unsigned h = __half_as_ushort(__float2half_rn(__uint_as_float(vals[i])));
         post[i] = ((uint32_t)h << 16) | (uint32_t)(keys[i] & 0xffffu);
     }
 }
@@ -55,10 +59,17 @@ __global__ void postings_pack_kernel(int64_t nnz, const uint64_t *__restrict__ k
 __device__ __forceinline__ float post_w(uint32_t e) { return __half2float(__ushort_as_half((unsigned short)(e >> 16))); }
 __device__ __forceinline__ int post_c(uint32_t e) { return (int)(e & 0xffffu); }
 
-// bucket directory: one aligned 8-byte {start, length} per (tile, feature) so that a lane fetches it in one load
-__global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr, int2 *__restrict__ dir) {
+// bucket directory: one aligned 8-byte entry per (feature, tile) so that a lane fetches it in one load:
+// {int32 start, u16 length | fp16 largest |weight| << 16}
+__global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ maxw,
+                                    int2 *__restrict__ dir) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nb) dir[i] = make_int2(ptr[i], ptr[i + 1] - ptr[i]);
+    if (i < nb) dir[i] = make_int2(ptr[i], (int)(((uint32_t)(ptr[i + 1] - ptr[i]) & 0xffffu) | (maxw[i] << 16)));
+}
+
+__device__ __forceinline__ int dir_len(int2 d) { return d.y & 0xffff; }
+__device__ __forceinline__ float dir_maxw(int2 d) {
+    return __half2float(__ushort_as_half((unsigned short)((unsigned)d.y >> 16)));
 }
 
 // ---------------------------------------------------------------------------
@@ -241,36 +252,46 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         // tile ids, directory slots (T * V1 < 2^31, checked by sg_postings_build) and positions fit 32 bits
         const int t_begin = (int)(group * tiles_per_group);
         const int t_end = (int)(t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T);
-        const int v1 = (int)V1;
+        const int n_tiles = (int)T;
 
-        // the first 32 features of the row stay in registers; their directory entries for the next
-        // column tile are fetched while the current tile is processed
+        // the first 32 features of the row stay in registers; their directory entries (consecutive in the
+        // feature-major directory) for the next column tile are fetched while the current tile is processed
         int f0 = -1;
         float a0 = 0.f;
         if (lane < nf) {
             f0 = a_idx[p0 + lane];
             a0 = Ops::left_weight(a_val[p0 + lane] * a_scale);
         }
+        const int2 *drow = bdir + (f0 >= 0 ? f0 : 0) * n_tiles;
         int2 d_next = make_int2(0, 0);
-        if (f0 >= 0) d_next = bdir[t_begin * v1 + f0];
+        if (f0 >= 0) d_next = drow[t_begin];
 
         for (int t = t_begin; t < t_end; ++t) {
             const int2 d0 = d_next;
-            if (f0 >= 0 && t + 1 < t_end) d_next = bdir[(t + 1) * v1 + f0];
-            const val_t thr_c = Ops::threshold(xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r);
+            if (f0 >= 0 && t + 1 < t_end) d_next = drow[t + 1];
+            const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r;
+            if (nf <= 32) {
+                // Block-max test: no column of this tile can collect more than sum_f |a_f| * max|w_(f,tile)|.  If
+                // that cannot exceed the candidate threshold the tile is skipped: nothing is accumulated, so
+                // nothing has to be cleared or swept.  (Rows with more than 32 kept features are never skipped.)
+                float ub = fabsf(a0) * dir_maxw(d0);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) ub += __shfl_xor_sync(FULL, ub, o);
+                if (ub * 1.00001f <= Ops::left_weight(thr_f)) continue;
+            }
+            const val_t thr_c = Ops::threshold(thr_f);
             val_t seen = 0;        // largest value this lane wrote into the tile
-            apply_buckets<AccT>(acc, post, d0.x, d0.y, a0, lane, seen);
+            apply_buckets<AccT>(acc, post, d0.x, dir_len(d0), a0, lane, seen);
             if (nf > 32) {
-                const int2 *bd = bdir + t * v1;
                 for (int base = 32; base < nf; base += 32) {
                     const int k = base + lane;
                     int b0 = 0, len = 0;
                     float a = 0.f;
                     if (k < nf) {
-                        const int2 d = bd[a_idx[p0 + k]];
+                        const int2 d = bdir[a_idx[p0 + k] * n_tiles + t];
                         a = Ops::left_weight(a_val[p0 + k] * a_scale);
                         b0 = d.x;
-                        len = d.y;
+                        len = dir_len(d);
                     }
                     apply_buckets<AccT>(acc, post, b0, len, a, lane, seen);
                 }
@@ -526,7 +547,7 @@ size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles)
     cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
                                     (uint32_t *)nullptr, n);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t *)nullptr, (int32_t *)nullptr, nb);
-    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + align_up((size_t)nb * 4, 256) +
+    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + 2 * align_up((size_t)nb * 4, 256) +
            align_up(b1 > b2 ? b1 : b2, 256) + 4096;
 }
 
@@ -535,8 +556,8 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
                       int32_t *bucket_ptr, void *bucket_dir, void *postings, void *ws, size_t ws_bytes,
                       void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (tile_w <= 0 || (tile_w & 31) || tile_w > 65535)
-        return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 below 65536");
+    if (tile_w <= 0 || (tile_w & 31) || tile_w > 32768)
+        return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 up to 32768 (16-bit bucket lengths)");
     if (nnz >= (int64_t)0x7fffffff)
         return fail(SG_ERR_OVERFLOW, "right matrix nnz %lld does not fit int32 postings", (long long)nnz);
     const int64_t T = sg_num_tiles(n_rows, tile_w);
@@ -550,6 +571,7 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
     uint32_t *vals = ar.take<uint32_t>(n);
     uint32_t *vals_sorted = ar.take<uint32_t>(n);
     int32_t *cnt = ar.take<int32_t>((size_t)nb);
+    uint32_t *maxw = ar.take<uint32_t>((size_t)nb);
     size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_sorted, vals, vals_sorted, (int64_t)n);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, cnt, bucket_ptr, nb);
@@ -557,21 +579,24 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
     char *tmp = ar.take<char>(cub_bytes);
     if (!ar.ok()) return fail(SG_ERR_INVALID, "postings workspace too small (%zu < %zu)", ws_bytes, ar.off);
     SG_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nb * 4, st));
+    SG_CUDA_TRY(cudaMemsetAsync(maxw, 0, (size_t)nb * 4, st));
     if (n_rows > 0 && nnz > 0) {
         postings_keys_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, val32, rank, tile_w,
-                                                                         V1, indptr_base, keys, vals, cnt);
+                                                                         T, indptr_base, w_scale, keys, vals, cnt,
+                                                                         maxw);
         SG_LAUNCH_CHECK();
     }
     SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, cnt, bucket_ptr, nb, st));
     if (bucket_dir) {
-        postings_dir_kernel<<<(unsigned)((nb - 1 + 255) / 256), 256, 0, st>>>(nb - 1, bucket_ptr, (int2 *)bucket_dir);
+        postings_dir_kernel<<<(unsigned)((nb - 1 + 255) / 256), 256, 0, st>>>(nb - 1, bucket_ptr, maxw,
+                                                                              (int2 *)bucket_dir);
         SG_LAUNCH_CHECK();
     }
     if (nnz > 0) {
         const int bits = 16 + bits_for((uint64_t)(nb - 1));
         SG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, nnz, 0,
                                                     bits > 64 ? 64 : bits, st));
-        postings_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted, w_scale,
+        postings_pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, keys_sorted, vals_sorted,
                                                                             (uint32_t *)postings);
         SG_LAUNCH_CHECK();
     }
@@ -628,7 +653,7 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
     const int acc_bytes = acc_dtype == SG_ACC_U16 ? 2 : 4;
     if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 512)
         return fail(SG_ERR_INVALID, "tile_w * accumulator size must be a positive multiple of 512 bytes");
-    if (tile_w > 65536) return fail(SG_ERR_INVALID, "tile_w must not exceed 65536 (16-bit posting columns)");
+    if (tile_w > 32768) return fail(SG_ERR_INVALID, "tile_w must not exceed 32768 (16-bit bucket lengths)");
     if (!(cand_threshold >= 0.f)) return fail(SG_ERR_INVALID, "cand_threshold must be >= 0");
     int dev = 0, n_sm = 0, smem_optin = 0;
     SG_CUDA_TRY(cudaGetDevice(&dev));
