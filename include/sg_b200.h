@@ -105,8 +105,10 @@ int sg_tfidf_vocab_keys(const int32_t *df_table /*[dev]*/, const int32_t *rank_t
  * and the vstack over left blocks (:750).
  * ------------------------------------------------------------------------- */
 
-/* number of column tiles for `n_right` rows at `tile_w` columns per tile */
+/* number of column tiles for `n_right` rows at `tile_w` columns per tile; _padded: rounded up to a multiple of 64
+ * (row length of bucket_maxw, length of tile_bound) */
 int64_t sg_num_tiles(int64_t n_right, int tile_w);
+int64_t sg_num_tiles_padded(int64_t n_right, int tile_w);
 
 /*
  * Right matrix -> tile-major, column-sorted postings (the transpose that sp_matmul_topn performs on
@@ -117,8 +119,10 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w);
  * position - t*tile_w in the low 16 bits, the weight rounded to fp16 in the high 16 bits (candidate
  * scores only need to be within the caller's margin; every candidate is re-scored exactly).  `bucket_dir` (optional) receives the same directory as aligned
  * 8-byte entries {int32 start, u16 length, fp16 largest |weight| of the bucket}, T*(n_cols+1) of them, the form
- * sg_cossim_candidates reads: the largest weights let it skip every (left row, column tile) pair whose score
- * bound sum_f |a_f| * max|w_(f,t)| cannot reach the candidate threshold.  tile_w <= 32768.
+ * sg_cossim_candidates reads.  `bucket_maxw` receives the largest weights again as fp16 rows, one row of
+ * sg_num_tiles_padded() entries per feature (zero padded), which sg_cossim_candidates streams to skip every
+ * (left row, column tile) pair whose score bound sum_f |a_f| * max|w_(f,t)| cannot reach the candidate
+ * threshold.  tile_w <= 32768.
  * `indptr` may be a row-range view (indptr_base = indptr[0]).
  */
 size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles);
@@ -127,7 +131,8 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
                       const int32_t *rank /*[dev] or NULL*/, int tile_w, int64_t indptr_base,
                       float w_scale /* weights are multiplied by this before the fp16 rounding: 1 / max|w| */,
                       int32_t *bucket_ptr /*[dev] T*(n_cols+1)+1*/,
-                      void *bucket_dir /*[dev] T*(n_cols+1)*8 B or NULL*/, void *postings /*[dev] nnz*4 B*/,
+                      void *bucket_dir /*[dev] T*(n_cols+1)*8 B or NULL*/,
+                      void *bucket_maxw /*[dev] (n_cols+1)*Tp*2 B or NULL*/, void *postings /*[dev] nnz*4 B*/,
                       void *ws /*[dev]*/, size_t ws_bytes, void *stream);
 
 /*
@@ -174,7 +179,7 @@ int sg_tile_bounds(int64_t n_right, const int32_t *perm /*[dev] position -> row,
  * the number of candidates FOUND, which may exceed `cand_cap` (then only the
  * first cand_cap were stored and the caller re-runs with a larger buffer).
  * `row_queue` [dev] (zeroed) is the dynamic work queue over (column-tile group, left row) items,
- * groups outermost, `tiles_per_group` column tiles per group (sized by the caller so that one
+ * groups outermost, `tiles_per_group` column tiles per group (a multiple of 64, sized by the caller so that one
  * group's posting buckets stay L2-resident).
  */
 #define SG_ACC_F32 0
@@ -183,14 +188,15 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len
                          const int32_t *a_indices /*[dev]*/,
                          const float *a_val32 /*[dev]*/, int64_t row_begin, int64_t row_end,
                          const int32_t *perm_a /*[dev] processing order of the left rows, or NULL*/,
-                         int64_t n_right, int64_t n_cols, const void *bucket_dir /*[dev] {start,len} pairs*/,
+                         int64_t n_right, int64_t n_cols, const void *bucket_dir /*[dev] directory entries*/,
+                         const void *bucket_maxw /*[dev] fp16 rows of largest weights*/,
                          const void *postings /*[dev]*/,
                          const int32_t *perm_b /*[dev] position -> right row id, or NULL*/, int tile_w,
                          int acc_dtype,
                          float a_scale /* left weights are multiplied by this: the inverse of w_scale */,
                          float cand_threshold, const float *cand_threshold_row /*[dev] per row id, or NULL*/,
                          const float *pruned_norm_row /*[dev] per row id, or NULL*/,
-                         const float *tile_bound /*[dev] per column tile; required with pruned_norm_row*/,
+                         const float *tile_bound /*[dev] sg_num_tiles_padded() entries, zero padded*/,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
                          int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
                          unsigned long long *cand_count /*[dev] 1*/,

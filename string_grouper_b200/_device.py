@@ -18,8 +18,8 @@ LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "sym
 
 TRANSFER_BYTES = {"d2h": 0, "h2d": 0}      # bytes moved by the bulk copies (bench.py e2e accounting)
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 72 KB of accumulators per CTA, three CTAs per SM
-DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "16"))          # 16 warps x 3 CTAs at 40 registers (no spills)
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 512-byte accumulator tiles (256 columns of u16)
+DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "8"))           # 8 warps x 5 CTAs at 48 registers (no spills)
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
 U16_MARGIN_PER_FEATURE = 2e-5   # 1/32768 fixed-point accumulator tile: one rounding of <= 2^-16 per added product
@@ -218,20 +218,22 @@ def right_side(B, tile_w):
         nb = T * (n_cols + 1) + 1
         if nb >= 2**31 - 1:
             raise OverflowError("posting bucket table too large: %d features x %d tiles" % (n_cols, T))
+        Tp = int(L.sg_num_tiles_padded(n_rows, tile_w))
         bucket_ptr = _empty(nb, t.int32, B.device)
         bucket_dir = _empty(2 * nb, t.int32, B.device)
+        bucket_maxw = _empty((n_cols + 1) * Tp, t.float16, B.device)
         post = _empty(max(B.nnz, 1), t.int32, B.device)
         ws_bytes = int(L.sg_postings_workspace_bytes(B.nnz, n_cols, T))
         ws = _empty(ws_bytes, t.uint8, B.device)
         _lib.check(L.sg_postings_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
                                        _ptr(rank), tile_w, B.base, 1.0 / max(B.norm_bound, 1.0), _ptr(bucket_ptr),
-                                       _ptr(bucket_dir), _ptr(post),
+                                       _ptr(bucket_dir), _ptr(bucket_maxw), _ptr(post),
                                        _ptr(ws), ws_bytes, _stream()))
         LAUNCH_COUNTS["postings"] += 3
-        bound = _empty(T, t.float32, B.device)
+        bound = t.zeros(Tp, dtype=t.float32, device=B.device)
         _lib.check(L.sg_tile_bounds(n_rows, _ptr(perm), _ptr(B._heavy_norm), tile_w, _ptr(bound), _stream()))
         LAUNCH_COUNTS["prune"] += 1
-        B._postings2[tile_w] = (bucket_ptr, bucket_dir, post, T, bound)
+        B._postings2[tile_w] = (bucket_ptr, bucket_dir, bucket_maxw, post, T, bound)
     return (hrank, perm, rank) + B._postings2[tile_w]
 
 
@@ -288,10 +290,11 @@ class DeviceMatches:
 
 
 def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
-    """Column-tile width and warps per CTA.  Default: warps * tile_w * acc_bytes = 72 KB with 16 warps (three CTAs
-    per SM), 112 KB otherwise (two CTAs of 32 warps)."""
+    """Column-tile width and warps per CTA.  Default: 512-byte accumulator tiles (256 columns of 16-bit fixed
+    point): narrow tiles make the block-max test skip most (row, tile) pairs, and the test itself costs a
+    fraction of an instruction per pair."""
     warps = int(warps or DEFAULT_WARPS)
-    tile_w = int(tile_w or DEFAULT_TILE_W) or ((72 << 10) if warps == 16 else (112 << 10)) // (warps * acc_bytes)
+    tile_w = int(tile_w or DEFAULT_TILE_W) or 512 // acc_bytes
     q = 512 // acc_bytes                               # tile bytes must be a multiple of 512
     need = ((max(int(n_right), 1) + q - 1) // q) * q
     tile_w = max(q, min(tile_w, 32768) // q * q)
@@ -377,13 +380,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
-    hrank, perm_b, _, _, bucket_dir, post, T, tile_bound = right_side(B, tile_w)
+    hrank, perm_b, _, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:
         perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
-    # column tiles per work group: the group's posting buckets (8 B per stored value) should stay L2-resident
-    tiles_per_group = max(1, min(T, int(GROUP_BYTES // max(4 * B.nnz / T, 1))))
+    # column tiles per work group (a multiple of 64): the group's posting buckets should stay L2-resident
+    tiles_per_group = max(64, int(GROUP_BYTES // max(4 * B.nnz / T, 1)) // 64 * 64)
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
     dummy = _empty(1, t.int32, dev)
@@ -394,7 +397,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         counters.zero_()
         _lib.check(L.sg_cossim_candidates(
             _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
-            A.shape[1], _ptr(bucket_dir), _ptr(post), _ptr(perm_b), tile_w, acc_code, max(B.norm_bound, 1.0),
+            A.shape[1], _ptr(bucket_dir), _ptr(bucket_maxw), _ptr(post), _ptr(perm_b), tile_w, acc_code,
+            max(B.norm_bound, 1.0),
             thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity,
             c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1

@@ -43,14 +43,15 @@ SIGNATURES = {
     "sg_tfidf_finalize": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_tfidf_vocab_keys": (_i32, [_p, _p, _i32, _p, _p]),
     "sg_num_tiles": (_i64, [_i64, _i32]),
+    "sg_num_tiles_padded": (_i64, [_i64, _i32]),
     "sg_postings_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i32, _i64, _f32, _p, _p, _p, _p, _sz, _p]),
+    "sg_postings_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i32, _i64, _f32, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_feature_df": (_i32, [_i64, _i64, _p, _p, _p, _p]),
     "sg_prune_rows": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p]),
     "sg_heavy_norms": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p]),
     "sg_tile_bounds": (_i32, [_i64, _p, _p, _i32, _p, _p]),
-    "sg_cossim_candidates": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i32, _f32, _f32,
-                                    _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _i32, _p]),
+    "sg_cossim_candidates": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _f32,
+                                    _f32, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _i32, _p]),
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _sz, _p]),

@@ -62,9 +62,13 @@ __device__ __forceinline__ int post_c(uint32_t e) { return (int)(e & 0xffffu); }
 // bucket directory: one aligned 8-byte entry per (feature, tile) so that a lane fetches it in one load:
 // {int32 start, u16 length | fp16 largest |weight| << 16}
 __global__ void postings_dir_kernel(int64_t nb, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ maxw,
-                                    int2 *__restrict__ dir) {
+                                    int2 *__restrict__ dir, int64_t T, int64_t Tp,
+                                    unsigned short *__restrict__ maxw_rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nb) dir[i] = make_int2(ptr[i], (int)(((uint32_t)(ptr[i + 1] - ptr[i]) & 0xffffu) | (maxw[i] << 16)));
+    if (i >= nb) return;
+    dir[i] = make_int2(ptr[i], (int)(((uint32_t)(ptr[i + 1] - ptr[i]) & 0xffffu) | (maxw[i] << 16)));
+    // the same maxima as fp16 rows of Tp tiles per feature (zero padded): what the block-max test streams
+    if (maxw_rows) maxw_rows[(i / T) * Tp + (i % T)] = (unsigned short)maxw[i];
 }
 
 __device__ __forceinline__ int dir_len(int2 d) { return d.y & 0xffff; }
@@ -77,10 +81,9 @@ __device__ __forceinline__ float dir_maxw(int2 d) {
 // ---------------------------------------------------------------------------
 constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
 
-// Resident CTAs per SM the register allocation is made for: 2 x 32 warps at 32 registers per thread, or
-// 3 x 16 warps at 40 registers (no spills in the tile loop; the kernel is bound by the shared-memory pipe,
-// 48 warps hide the L2 latency of the posting reads as well as 64).
-constexpr int min_ctas(int nw) { return nw == 16 ? 3 : (64 / nw < 1 ? 1 : 64 / nw); }
+// Resident CTAs per SM the register allocation is made for (the accumulator tiles are small, registers decide):
+// 32 warps/CTA x 2 = 64 warps at 32 registers; 16 x 3 = 48 warps at 40; 8 x 5 = 40 warps at 48; 4 x 8 = 32 warps at 64.
+constexpr int min_ctas(int nw) { return nw == 32 ? 2 : nw == 16 ? 3 : nw == 8 ? 5 : 8; }
 
 // Accumulator tile element.
 //   float    : fp32 scores, read-modify-write in the long-bucket path, CAS-loop atomics in the short one.
@@ -205,14 +208,20 @@ __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint
 // features; a pair (i, j) is reported when its partial score exceeds
 //     thr_row[i] - xp_norm[i] * tile_bound[tile of j]
 // = the row's threshold minus what the pruned features can still add for the columns of that tile.
+//
+// Block-max test (`maxw_h`, the fp16 largest |weight| of every (feature, tile) bucket, feature-major, rows padded to
+// Tp tiles): no column of tile t can collect more than ub(t) = sum_f |a_f| * max|w_(f,t)|.  The bounds of 64 tiles
+// are evaluated at once, two tiles per lane in packed fp16 (one HFMA2 per kept feature and tile pair), and only
+// the tiles whose bound can exceed their candidate threshold are walked at all: nothing is accumulated, cleared
+// or swept for the others.
 template <int NW, typename AccT>
 __global__ void __launch_bounds__(NW * 32, min_ctas(NW))
 cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_len,
                          const int32_t *__restrict__ a_idx, const float *__restrict__ a_val, int64_t row_begin,
                          int64_t row_end, const int32_t *__restrict__ perm_a, int64_t n_right,
-                         const int2 *__restrict__ bdir, const uint32_t *__restrict__ post,
-                         const int32_t *__restrict__ perm_b, int64_t V1, int W, int64_t T,
-                         int64_t tiles_per_group, float a_scale, float thr_all,
+                         const int2 *__restrict__ bdir, const uint32_t *__restrict__ maxw_h,
+                         const uint32_t *__restrict__ post, const int32_t *__restrict__ perm_b, int Tp, int W,
+                         int64_t T, int64_t tiles_per_group, float a_scale, float thr_all,
                          const float *__restrict__ thr_row, const float *__restrict__ xp_norm,
                          const float *__restrict__ tile_bound, int32_t *__restrict__ cand_row,
                          int32_t *__restrict__ cand_col, unsigned long long cap,
@@ -224,7 +233,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
     const int warp = threadIdx.x >> 5;
     AccT *acc = reinterpret_cast<AccT *>(smem_raw) + (size_t)warp * W;
     uint4 *acc16 = reinterpret_cast<uint4 *>(acc);
-    const int n16 = W / Ops::PER16;                         // 16-byte vectors per tile, a multiple of 32
+    const int n16 = W / Ops::PER16;                         // 16-byte vectors per tile
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
     for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
@@ -232,10 +241,11 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
 
     // Work item = (column-tile group, left row), groups outermost: at any moment every CTA of the grid streams
     // posting buckets of the same few column tiles, so the live posting set stays L2-resident however
-    // large the right matrix is.
+    // large the right matrix is.  tiles_per_group is a multiple of 64.
     const int64_t n_rows = row_end - row_begin;
     const int64_t n_groups = (T + tiles_per_group - 1) / tiles_per_group;
     const unsigned long long n_items = (unsigned long long)n_rows * (unsigned long long)n_groups;
+    const int n_tiles = (int)T;
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(row_queue, 1ull);
@@ -243,7 +253,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         if (item >= n_items) break;
         const int64_t group = (int64_t)(item / (unsigned long long)n_rows);
         const int64_t ridx = (int64_t)(item % (unsigned long long)n_rows);
-        const int64_t row = perm_a ? perm_a[ridx] : row_begin + ridx;   // signature order: neighbours share buckets
+        const int64_t row = perm_a ? perm_a[ridx] : row_begin + ridx;   // processing order: neighbours share buckets
         const int64_t p0 = a_indptr[row];
         const int nf = a_len ? a_len[row] : (int)(a_indptr[row + 1] - p0);
         if (nf == 0) continue;
@@ -252,89 +262,120 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
         // tile ids, directory slots (T * V1 < 2^31, checked by sg_postings_build) and positions fit 32 bits
         const int t_begin = (int)(group * tiles_per_group);
         const int t_end = (int)(t_begin + tiles_per_group < T ? t_begin + tiles_per_group : T);
-        const int n_tiles = (int)T;
 
-        // the first 32 features of the row stay in registers; their directory entries (consecutive in the
-        // feature-major directory) for the next column tile are fetched while the current tile is processed
-        int f0 = -1;
+        // the first 32 features of the row stay in registers
+        int f0 = 0;
         float a0 = 0.f;
+        __half2 a2 = __float2half2_rn(0.f);
         if (lane < nf) {
             f0 = a_idx[p0 + lane];
-            a0 = Ops::left_weight(a_val[p0 + lane] * a_scale);
+            const float a = a_val[p0 + lane] * a_scale;
+            a0 = Ops::left_weight(a);
+            a2 = __half2half2(__float2half_ru(fabsf(a)));   // rounded up: the bound must not fall short
         }
-        const int2 *drow = bdir + (f0 >= 0 ? f0 : 0) * n_tiles;
-        int2 d_next = make_int2(0, 0);
-        if (f0 >= 0) d_next = drow[t_begin];
+        const int2 *drow = bdir + f0 * n_tiles;
+        const int nk = nf < 32 ? nf : 32;
+        // fp16 arithmetic of the bound: one rounding of at most 2^-11 (values below 2) per kept feature
+        const float slack = 5e-4f * (float)nk + 1e-4f;
 
-        for (int t = t_begin; t < t_end; ++t) {
-            const int2 d0 = d_next;
-            if (f0 >= 0 && t + 1 < t_end) d_next = drow[t + 1];
-            const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r;
+        for (int tb = t_begin; tb < t_end; tb += 64) {
+            // ---- bounds of tiles tb + 2*lane and tb + 2*lane + 1
+            unsigned m_even, m_odd;
             if (nf <= 32) {
-                // Block-max test: no column of this tile can collect more than sum_f |a_f| * max|w_(f,tile)|.  If
-                // that cannot exceed the candidate threshold the tile is skipped: nothing is accumulated, so
-                // nothing has to be cleared or swept.  (Rows with more than 32 kept features are never skipped.)
-                float ub = fabsf(a0) * dir_maxw(d0);
-#pragma unroll
-                for (int o = 16; o; o >>= 1) ub += __shfl_xor_sync(FULL, ub, o);
-                if (ub * 1.00001f <= Ops::left_weight(thr_f)) continue;
-            }
-            const val_t thr_c = Ops::threshold(thr_f);
-            val_t seen = 0;        // largest value this lane wrote into the tile
-            apply_buckets<AccT>(acc, post, d0.x, dir_len(d0), a0, lane, seen);
-            if (nf > 32) {
-                for (int base = 32; base < nf; base += 32) {
-                    const int k = base + lane;
-                    int b0 = 0, len = 0;
-                    float a = 0.f;
-                    if (k < nf) {
-                        const int2 d = bdir[a_idx[p0 + k] * n_tiles + t];
-                        a = Ops::left_weight(a_val[p0 + k] * a_scale);
-                        b0 = d.x;
-                        len = dir_len(d);
-                    }
-                    apply_buckets<AccT>(acc, post, b0, len, a, lane, seen);
+                __half2 ub2 = __float2half2_rn(0.f);
+                const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
+                for (int k = 0; k < nk; ++k) {
+                    const int fk = __shfl_sync(FULL, f0, k);
+                    const __half2 ak2 = __shfl_sync(FULL, a2, k);
+                    const uint32_t m = mrow[fk * (Tp >> 1)];
+                    ub2 = __hfma2(ak2, *reinterpret_cast<const __half2 *>(&m), ub2);
                 }
+                const float2 ub = __half22float2(ub2);
+                const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
+                const int t0 = tb + 2 * lane;
+                const float thr0 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.x, thr_r), 0.f) : thr_r;
+                const float thr1 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.y, thr_r), 0.f) : thr_r;
+                m_even = __ballot_sync(FULL, t0 < t_end && ub.x + slack > thr0);
+                m_odd = __ballot_sync(FULL, t0 + 1 < t_end && ub.y + slack > thr1);
+            } else {        // rows with more than 32 kept features: every tile is walked
+                const int t0 = tb + 2 * lane;
+                m_even = __ballot_sync(FULL, t0 < t_end);
+                m_odd = __ballot_sync(FULL, t0 + 1 < t_end);
             }
-            // No value written into this tile exceeded the candidate threshold (the common case):
-            // clearing is enough, the tile need not be read back.
-            if (!__any_sync(FULL, seen > thr_c)) {
-                for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
-                __syncwarp();
-                continue;
-            }
-            // sweep: report scores above the candidate threshold, clear the tile; one atomic per warp step
-            for (int c = lane; c < n16; c += 32) {
-                const uint4 v = acc16[c];
-                unsigned m = 0;
-                if (v.x | v.y | v.z | v.w) {
-                    acc16[c] = zero4;
-                    m = Ops::above(v, thr_c);
-                }
-                if (__any_sync(FULL, m != 0)) {
-                    const int cnt = __popc(m);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int up = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    unsigned long long slot = 0;
-                    if (lane == 31) slot = atomicAdd(cand_count, (unsigned long long)incl);
-                    slot = __shfl_sync(FULL, slot, 31) + (unsigned long long)(incl - cnt);
-                    while (m) {
-                        const int i = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (slot < cap) {
-                            const int col = t * W + c * Ops::PER16 + i;
-                            cand_row[slot] = (int32_t)row;
-                            cand_col[slot] = perm_b ? perm_b[col] : col;
+            // ---- walk the surviving tiles; the directory entry of the next one is fetched ahead
+            int t = -1;
+            if (m_even) { t = tb + 2 * (__ffs(m_even) - 1); m_even &= m_even - 1; }
+            else if (m_odd) { t = tb + 2 * (__ffs(m_odd) - 1) + 1; m_odd &= m_odd - 1; }
+            int2 d_cur = make_int2(0, 0);
+            if (t >= 0 && lane < nf) d_cur = drow[t];
+            while (t >= 0) {
+                int t_next = -1;
+                if (m_even) { t_next = tb + 2 * (__ffs(m_even) - 1); m_even &= m_even - 1; }
+                else if (m_odd) { t_next = tb + 2 * (__ffs(m_odd) - 1) + 1; m_odd &= m_odd - 1; }
+                int2 d_next = make_int2(0, 0);
+                if (t_next >= 0 && lane < nf) d_next = drow[t_next];
+
+                const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r;
+                const val_t thr_c = Ops::threshold(thr_f);
+                val_t seen = 0;        // largest value this lane wrote into the tile
+                apply_buckets<AccT>(acc, post, d_cur.x, dir_len(d_cur), a0, lane, seen);
+                if (nf > 32) {
+                    for (int base = 32; base < nf; base += 32) {
+                        const int k = base + lane;
+                        int b0 = 0, len = 0;
+                        float a = 0.f;
+                        if (k < nf) {
+                            const int2 d = bdir[a_idx[p0 + k] * n_tiles + t];
+                            a = Ops::left_weight(a_val[p0 + k] * a_scale);
+                            b0 = d.x;
+                            len = dir_len(d);
                         }
-                        ++slot;
+                        apply_buckets<AccT>(acc, post, b0, len, a, lane, seen);
                     }
                 }
+                if (!__any_sync(FULL, seen > thr_c)) {
+                    // No value written into this tile exceeded the candidate threshold: clearing is enough
+                    for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
+                } else {
+                    // sweep: report scores above the candidate threshold, clear the tile; one atomic per warp step
+                    for (int c0 = 0; c0 < n16; c0 += 32) {
+                        const int c = c0 + lane;
+                        unsigned m = 0;
+                        if (c < n16) {
+                            const uint4 v = acc16[c];
+                            if (v.x | v.y | v.z | v.w) {
+                                acc16[c] = zero4;
+                                m = Ops::above(v, thr_c);
+                            }
+                        }
+                        if (__any_sync(FULL, m != 0)) {
+                            const int cnt = __popc(m);
+                            int incl = cnt;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int up = __shfl_up_sync(FULL, incl, o);
+                                if (lane >= o) incl += up;
+                            }
+                            unsigned long long slot = 0;
+                            if (lane == 31) slot = atomicAdd(cand_count, (unsigned long long)incl);
+                            slot = __shfl_sync(FULL, slot, 31) + (unsigned long long)(incl - cnt);
+                            while (m) {
+                                const int i = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (slot < cap) {
+                                    const int col = t * W + c * Ops::PER16 + i;
+                                    cand_row[slot] = (int32_t)row;
+                                    cand_col[slot] = perm_b ? perm_b[col] : col;
+                                }
+                                ++slot;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                t = t_next;
+                d_cur = d_next;
             }
-            __syncwarp();
         }
     }
 }
@@ -551,10 +592,14 @@ size_t sg_postings_workspace_bytes(int64_t nnz, int64_t n_cols, int64_t n_tiles)
            align_up(b1 > b2 ? b1 : b2, 256) + 4096;
 }
 
+int64_t sg_num_tiles_padded(int64_t n_right, int tile_w) {
+    return (sg_num_tiles(n_right, tile_w) + 63) / 64 * 64;
+}
+
 int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr, const int32_t *indices,
                       const float *val32, const int32_t *rank, int tile_w, int64_t indptr_base, float w_scale,
-                      int32_t *bucket_ptr, void *bucket_dir, void *postings, void *ws, size_t ws_bytes,
-                      void *stream_) {
+                      int32_t *bucket_ptr, void *bucket_dir, void *bucket_maxw, void *postings, void *ws,
+                      size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (tile_w <= 0 || (tile_w & 31) || tile_w > 32768)
         return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 up to 32768 (16-bit bucket lengths)");
@@ -588,8 +633,11 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
     }
     SG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, cnt, bucket_ptr, nb, st));
     if (bucket_dir) {
+        const int64_t Tp = sg_num_tiles_padded(n_rows, tile_w);
+        if (bucket_maxw) SG_CUDA_TRY(cudaMemsetAsync(bucket_maxw, 0, (size_t)(V1 * Tp) * 2, st));
         postings_dir_kernel<<<(unsigned)((nb - 1 + 255) / 256), 256, 0, st>>>(nb - 1, bucket_ptr, maxw,
-                                                                              (int2 *)bucket_dir);
+                                                                              (int2 *)bucket_dir, T, Tp,
+                                                                              (unsigned short *)bucket_maxw);
         SG_LAUNCH_CHECK();
     }
     if (nnz > 0) {
@@ -608,8 +656,9 @@ int sg_postings_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t
 template <int NW, typename AccT>
 static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, const int32_t *a_indices,
                              const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
-                             int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
-                             const int32_t *perm_b, int tile_w, int64_t tiles_per_group, float a_scale,
+                             int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *bucket_maxw,
+                             const void *postings, const int32_t *perm_b, int tile_w, int64_t tiles_per_group,
+                             float a_scale,
                              float thr_c, const float *thr_row, const float *xp_norm, const float *tile_bound,
                              int32_t *cand_row, int32_t *cand_col,
                              int64_t cand_cap, unsigned long long *cand_count, unsigned long long *row_queue,
@@ -628,7 +677,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
     if (ctas < 1) ctas = 1;
     cossim_candidates_kernel<NW, AccT><<<(unsigned)ctas, NW * 32, smem, st>>>(
         a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
-        (const uint32_t *)postings, perm_b, n_cols + 1, tile_w, T, tiles_per_group < 1 ? 1 : tiles_per_group,
+        (const uint32_t *)bucket_maxw, (const uint32_t *)postings, perm_b, (int)sg_num_tiles_padded(n_right, tile_w),
+        tile_w, T, tiles_per_group,
         a_scale, thr_c, thr_row, xp_norm, tile_bound, cand_row, cand_col, (unsigned long long)cand_cap, cand_count,
         row_queue);
     SG_LAUNCH_CHECK();
@@ -639,8 +689,9 @@ extern "C" {
 
 int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const int32_t *a_indices,
                          const float *a_val32, int64_t row_begin, int64_t row_end, const int32_t *perm_a,
-                         int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *postings,
-                         const int32_t *perm_b, int tile_w, int acc_dtype, float a_scale, float cand_threshold,
+                         int64_t n_right, int64_t n_cols, const void *bucket_dir, const void *bucket_maxw,
+                         const void *postings, const int32_t *perm_b, int tile_w, int acc_dtype, float a_scale,
+                         float cand_threshold,
                          const float *cand_threshold_row, const float *pruned_norm_row, const float *tile_bound,
                          int64_t tiles_per_group, int32_t *cand_row,
                          int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
@@ -649,7 +700,9 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
     if (row_end <= row_begin || n_right <= 0) return SG_OK;
     if (acc_dtype != SG_ACC_F32 && acc_dtype != SG_ACC_U16)
         return fail(SG_ERR_INVALID, "acc_dtype must be SG_ACC_F32 or SG_ACC_U16");
-    if (pruned_norm_row && !tile_bound) return fail(SG_ERR_INVALID, "pruned_norm_row needs tile_bound");
+    if (!tile_bound || !bucket_maxw) return fail(SG_ERR_INVALID, "tile_bound and bucket_maxw are required");
+    if (tiles_per_group < 64 || tiles_per_group % 64)
+        return fail(SG_ERR_INVALID, "tiles_per_group must be a positive multiple of 64");
     const int acc_bytes = acc_dtype == SG_ACC_U16 ? 2 : 4;
     if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 512)
         return fail(SG_ERR_INVALID, "tile_w * accumulator size must be a positive multiple of 512 bytes");
@@ -663,8 +716,8 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
         return fail(SG_ERR_INVALID, "warps_per_cta*tile_w*%d = %zu exceeds %d bytes of shared memory", acc_bytes,
                     (size_t)warps_per_cta * tile_w * acc_bytes, smem_optin);
 #define SG_ARGS                                                                                              \
-    a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, postings, \
-        perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, pruned_norm_row,      \
+    a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, bucket_maxw, \
+        postings, perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, pruned_norm_row,      \
         tile_bound, cand_row, cand_col, cand_cap, cand_count, row_queue, n_sm, st
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
