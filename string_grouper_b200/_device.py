@@ -28,6 +28,7 @@ U16_MARGIN_PER_FEATURE = 2e-5   # 1/32768 fixed-point accumulator tile: one roun
 PRUNE_FRAC = float(os.environ.get("SG_B200_PRUNE", "0.9"))
 ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulator tile: u16 | f32
 MAX_CAND_DENSITY = float(os.environ.get("SG_B200_MAX_CAND_DENSITY", "1.5e-3"))   # candidates per (row, column) pair
+MAX_BUCKETS = int(os.environ.get("SG_B200_MAX_BUCKETS", str(400_000_000)))       # directory entries (22 B each)
 CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
 
 
@@ -295,7 +296,7 @@ def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
     fraction of an instruction per pair."""
     warps = int(warps or DEFAULT_WARPS)
     tile_w = int(tile_w or DEFAULT_TILE_W) or 512 // acc_bytes
-    q = 512 // acc_bytes                               # tile bytes must be a multiple of 512
+    q = 256 // acc_bytes                               # tile bytes must be a multiple of 256
     need = ((max(int(n_right), 1) + q - 1) // q) * q
     tile_w = max(q, min(tile_w, 32768) // q * q)
     return min(tile_w, need), warps
@@ -378,6 +379,9 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
     tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
+    # the bucket directory holds one entry per (feature, tile): widen the tiles until it stays below MAX_BUCKETS
+    while (-(-n_right // tile_w)) * (B.shape[1] + 1) > MAX_BUCKETS and tile_w < 32768:
+        tile_w *= 2
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
     hrank, perm_b, _, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)

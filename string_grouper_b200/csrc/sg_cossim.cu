@@ -704,8 +704,8 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
     if (tiles_per_group < 64 || tiles_per_group % 64)
         return fail(SG_ERR_INVALID, "tiles_per_group must be a positive multiple of 64");
     const int acc_bytes = acc_dtype == SG_ACC_U16 ? 2 : 4;
-    if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 512)
-        return fail(SG_ERR_INVALID, "tile_w * accumulator size must be a positive multiple of 512 bytes");
+    if (tile_w <= 0 || ((size_t)tile_w * acc_bytes) % 256 || (tile_w & 31))
+        return fail(SG_ERR_INVALID, "tile_w must be a multiple of 32 and tile_w * accumulator size a multiple of 256 bytes");
     if (tile_w > 32768) return fail(SG_ERR_INVALID, "tile_w must not exceed 32768 (16-bit bucket lengths)");
     if (!(cand_threshold >= 0.f)) return fail(SG_ERR_INVALID, "cand_threshold must be >= 0");
     int dev = 0, n_sm = 0, smem_optin = 0;
