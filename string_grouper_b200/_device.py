@@ -101,6 +101,8 @@ class DeviceCSR:
         self._host = None
         self._order = None          # (hrank, perm, rank) in heavy-feature signature order
         self._postings2 = {}
+        self.row_offset = None      # set when this matrix is one rank's block of rows of a sharded matrix
+        self.global_rows = None
         self._df = None             # document frequency of every feature (sg_feature_df)
         self._heavy_norm = None     # per-row norm over the heavy features (sg_heavy_norms)
         self.nonneg = True          # no negative stored value (K1 output; checked for uploaded matrices)
