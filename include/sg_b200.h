@@ -278,6 +278,15 @@ int sg_group_reps(int64_t n, int64_t nnz, const int32_t *row, const int32_t *col
                   int centroid, int32_t *rep /*[dev] n*/, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Nearest master per duplicate.  Replaces the reduction of StringGrouper._get_nearest_matches
+ * (sg.py:783-849; the groupby / idxmax of :803-807): best[j] = left row with the highest similarity to right row j,
+ * the smallest left index among equal scores, -1 when no match holds j.  Input: the match list in any order.
+ * ------------------------------------------------------------------------- */
+size_t sg_nearest_master_workspace_bytes(int64_t n_right);
+int sg_nearest_master(int64_t nnz, const int32_t *row, const int32_t *col, const double *score, int64_t n_right,
+                      int32_t *best /*[dev] n_right*/, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * String gather for get_matches: replaces `Series.iloc[matches_list.master_side]` /
  * `.iloc[matches_list.dupe_side]` (sg.py:462, :467) for strings that are resident in HBM as packed UTF-8.
  * positions[i] is a row of the Series that starts at document `doc_base` of the packed buffer.

@@ -564,6 +564,21 @@ def group_reps(M, n, centroid):
     return rep[:n].cpu().numpy().astype(np.int64)
 
 
+def nearest_master(M, n_right):
+    """int64 [n_right]: for every right row the left row of its best match (smallest index among equal scores),
+    -1 without a match — the reduction of StringGrouper._get_nearest_matches (string_grouper.py:803-807)."""
+    t = require_cuda()
+    L = _lib.load()
+    dev = M.d_row.device
+    best = _empty(n_right, t.int32, dev)
+    ws_bytes = int(L.sg_nearest_master_workspace_bytes(n_right))
+    ws = _empty(ws_bytes, t.uint8, dev)
+    _lib.check(L.sg_nearest_master(M.nnz, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), n_right, _ptr(best), _ptr(ws),
+                                   ws_bytes, _stream()))
+    LAUNCH_COUNTS["groups"] += 3
+    return best[:n_right].cpu().numpy().astype(np.int64)
+
+
 class RawStrings:
     """Packed UTF-8 strings of master ++ duplicates as uploaded for K1, kept for the device string gather."""
 

@@ -113,6 +113,33 @@ __global__ void cc_assign_kernel(int64_t n, const int32_t *__restrict__ label, c
     if (i < n) rep[i] = rep_of_root ? rep_of_root[label[i]] : label[i];
 }
 
+// ---------------------------------------------------------------------------
+// nearest master per duplicate (StringGrouper._get_nearest_matches, string_grouper.py:783-849, the reduction of
+// :803-807): for every right row the left row with the highest similarity, the smallest left index among equals.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);      // order-preserving map of IEEE doubles to unsigned
+}
+
+__global__ void nearest_score_kernel(int64_t nnz, const int32_t *__restrict__ col, const double *__restrict__ score,
+                                     unsigned long long *__restrict__ best_bits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) atomicMax(best_bits + col[i], ordered_bits(score[i]));
+}
+
+__global__ void nearest_row_kernel(int64_t nnz, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                   const double *__restrict__ score, const unsigned long long *__restrict__ best_bits,
+                                   int32_t *__restrict__ best_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz && ordered_bits(score[i]) == best_bits[col[i]]) atomicMin(best_row + col[i], row[i]);
+}
+
+__global__ void nearest_finish_kernel(int64_t n, int32_t *__restrict__ best_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && best_row[i] == 0x7fffffff) best_row[i] = -1;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -164,6 +191,36 @@ int sg_group_reps(int64_t n, int64_t nnz, const int32_t *row, const int32_t *col
         cc_assign_kernel<<<gn, 256, 0, st>>>(n, label, nullptr, rep);
     }
     SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+size_t sg_nearest_master_workspace_bytes(int64_t n_right) {
+    return align_up((size_t)(n_right + 1) * 8, 256) + 1024;
+}
+
+// best[j] = left row with the highest similarity to right row j (smallest left index among equal scores), -1 when
+// no match holds j.  Input: a match list in any order.
+int sg_nearest_master(int64_t nnz, const int32_t *row, const int32_t *col, const double *score, int64_t n_right,
+                      int32_t *best, void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_right <= 0) return SG_OK;
+    Arena ar(ws, ws_bytes);
+    unsigned long long *best_bits = ar.take<unsigned long long>((size_t)n_right + 1);
+    if (!ar.ok()) return fail(SG_ERR_INVALID, "nearest workspace too small (%zu < %zu)", ws_bytes, ar.off);
+    SG_CUDA_TRY(cudaMemsetAsync(best_bits, 0, (size_t)n_right * 8, st));
+    SG_CUDA_TRY(cudaMemsetAsync(best, 0xff, (size_t)n_right * 4, st));
+    if (nnz > 0) {
+        const unsigned ge = (unsigned)((nnz + 255) / 256);
+        const unsigned gn = (unsigned)((n_right + 255) / 256);
+        nearest_score_kernel<<<ge, 256, 0, st>>>(nnz, col, score, best_bits);
+        SG_LAUNCH_CHECK();
+        // 0x7fffffff = "no row yet" for the atomicMin of the second pass
+        SG_CUDA_TRY(cudaMemsetAsync(best, 0x7f, (size_t)n_right * 4, st));
+        nearest_row_kernel<<<ge, 256, 0, st>>>(nnz, row, col, score, best_bits, best);
+        SG_LAUNCH_CHECK();
+        nearest_finish_kernel<<<gn, 256, 0, st>>>(n_right, best);
+        SG_LAUNCH_CHECK();
+    }
     return SG_OK;
 }
 

@@ -494,7 +494,11 @@ class StringGrouper(object):
         n_dup = len(self._duplicates)
         pairs = self._matches_list
         best = np.full(n_dup, -1, dtype=np.int64)
-        if len(pairs):
+        dev = self._matches_device
+        if dev is not None and len(pairs) == dev.nnz and n_dup > 0:
+            # the match list is still in HBM: arg-max per duplicate there (csrc/sg_groups.cu)
+            best = _device.nearest_master(dev, n_dup)
+        elif len(pairs):
             d = pairs.dupe_side.to_numpy()
             m = pairs.master_side.to_numpy()
             s = pairs.similarity.to_numpy()

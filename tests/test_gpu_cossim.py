@@ -192,3 +192,25 @@ def test_rowwise_dot():
     ref = np.asarray(m.multiply(d).sum(axis=1)).squeeze(axis=1)
     got = D.rowwise_dot(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(d))
     np.testing.assert_allclose(got, ref, atol=1e-12)
+
+
+def test_nearest_master_matches_host_rule():
+    """sg_nearest_master: per right row the left row with the highest score, smallest index among equals."""
+    import torch
+    from string_grouper_b200 import _device as D
+    rng = np.random.default_rng(3)
+    n_left, n_right, nnz = 5000, 3000, 40000
+    r = rng.integers(0, n_left, nnz).astype(np.int32)
+    c = rng.integers(0, n_right - 100, nnz).astype(np.int32)          # the last 100 right rows stay unmatched
+    s = np.round(rng.random(nnz), 2)                                   # many exact ties
+    dev = torch.device("cuda", torch.cuda.current_device())
+    M = D.DeviceMatches((n_left, n_right), torch.from_numpy(r).to(dev), torch.from_numpy(c).to(dev),
+                        torch.from_numpy(s).to(dev), nnz, 0)
+    got = D.nearest_master(M, n_right)
+    order = np.lexsort((r, -s, c))
+    first = np.ones(nnz, dtype=bool)
+    first[1:] = c[order][1:] != c[order][:-1]
+    want = np.full(n_right, -1, dtype=np.int64)
+    want[c[order][first]] = r[order][first]
+    assert np.array_equal(got, want)
+    assert np.all(got[-100:] == -1)
