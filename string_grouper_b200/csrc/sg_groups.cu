@@ -137,7 +137,7 @@ __global__ void nearest_row_kernel(int64_t nnz, const int32_t *__restrict__ row,
 
 __global__ void nearest_finish_kernel(int64_t n, int32_t *__restrict__ best_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && best_row[i] == 0x7fffffff) best_row[i] = -1;
+    if (i < n && best_row[i] == 0x7f7f7f7f) best_row[i] = -1;      // the byte-wise 0x7f fill = "no row yet"
 }
 
 }  // namespace sg
@@ -214,7 +214,7 @@ int sg_nearest_master(int64_t nnz, const int32_t *row, const int32_t *col, const
         const unsigned gn = (unsigned)((n_right + 255) / 256);
         nearest_score_kernel<<<ge, 256, 0, st>>>(nnz, col, score, best_bits);
         SG_LAUNCH_CHECK();
-        // 0x7fffffff = "no row yet" for the atomicMin of the second pass
+        // 0x7f7f7f7f = "no row yet" for the atomicMin of the second pass (left row ids are far below it)
         SG_CUDA_TRY(cudaMemsetAsync(best, 0x7f, (size_t)n_right * 4, st));
         nearest_row_kernel<<<ge, 256, 0, st>>>(nnz, row, col, score, best_bits, best);
         SG_LAUNCH_CHECK();
