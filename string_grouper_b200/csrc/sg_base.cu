@@ -23,7 +23,7 @@ extern "C" {
 
 const char *sg_last_error(void) { return sg::err_buf(); }
 
-int sg_abi_version(void) { return 2; }
+int sg_abi_version(void) { return 3; }
 
 int sg_device_info(int *sm_count, int *smem_optin_bytes, int *l2_bytes) {
     int dev = 0;

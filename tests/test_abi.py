@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_pure_host_entry_points():
     lib = _lib.load()
-    assert lib.sg_abi_version() == 2
+    assert lib.sg_abi_version() == 3
     assert lib.sg_num_tiles(10_000, 3072) == 4 and lib.sg_num_tiles(0, 128) == 1
     assert lib.sg_tfidf_table_slots(3) == 2 ** 21 and lib.sg_tfidf_table_slots(5) == -1
 
