@@ -236,7 +236,7 @@ def right_side(B, tile_w):
         bound = t.zeros(Tp, dtype=t.float32, device=B.device)
         _lib.check(L.sg_tile_bounds(n_rows, _ptr(perm), _ptr(B._heavy_norm), tile_w, _ptr(bound), _stream()))
         LAUNCH_COUNTS["prune"] += 1
-        B._postings2[tile_w] = (bucket_ptr, bucket_dir, bucket_maxw, post, T, bound)
+        B._postings2[tile_w] = (bucket_dir, bucket_maxw, post, T, bound)     # bucket_ptr is only needed for the build
     return (hrank, perm, rank) + B._postings2[tile_w]
 
 
@@ -386,7 +386,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         tile_w *= 2
     # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
     # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
-    hrank, perm_b, _, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
+    hrank, perm_b, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:

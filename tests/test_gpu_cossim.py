@@ -122,6 +122,13 @@ def test_row_chunks_and_adaptive_pruning_level(monkeypatch):
     assert st["n_row_chunks"] > 1
     for x, y in zip(b, got.host_triples()):
         assert np.array_equal(x, y)
+    # a bucket directory that would exceed MAX_BUCKETS entries makes the tiles wider
+    st3 = {}
+    monkeypatch.setattr(D, "MAX_BUCKETS", 2_000_000)
+    got3 = D.cossim_topn(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(m), 20, 0.8, stats=st3)
+    assert st3["tile_w"] > st["tile_w"]
+    for x, y in zip(b, got3.host_triples()):
+        assert np.array_equal(x, y)
     st2 = {}
     monkeypatch.setattr(D, "MAX_CAND_DENSITY", 1e-7)
     got2 = D.cossim_topn(A, A, 20, 0.8, stats=st2)
