@@ -99,7 +99,7 @@ class DeviceCSR:
         self.dtype = np.dtype(dtype)
         self.norm_bound = float(norm_bound)
         self._host = None
-        self._order = None          # (hrank, perm, rank) in heavy-feature signature order
+        self._order = None          # (hrank, perm, rank): rows ordered by (quantised heavy norm, heavy-feature signature)
         self._postings2 = {}
         self.row_offset = None      # set when this matrix is one rank's block of rows of a sharded matrix
         self.global_rows = None
@@ -206,7 +206,8 @@ def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True, row_norm=None
 
 
 def right_side(B, tile_w):
-    """Signature order + tile-major column-sorted postings of the right matrix, cached on B."""
+    """Row order (heavy norm, signature), feature-major column-sorted postings, bucket directory with block maxima and
+    per-tile pruning bounds of the right matrix, cached on B."""
     t = require_cuda()
     L = _lib.load()
     if B._order is None:
@@ -384,8 +385,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     # the bucket directory holds one entry per (feature, tile): widen the tiles until it stays below MAX_BUCKETS
     while (-(-n_right // tile_w)) * (B.shape[1] + 1) > MAX_BUCKETS and tile_w < 32768:
         tile_w *= 2
-    # both operands in heavy-feature signature order: neighbouring left rows stream the same buckets, and
-    # the docs of a frequent feature are runs of consecutive columns (bank-conflict-free accumulation)
+    # both operands in the same processing order (quantised heavy norm, heavy-feature signature): neighbouring left
+    # rows stream the same buckets, and the rows of a column tile have similar heavy norms (tight per-tile bound)
     hrank, perm_b, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b

@@ -5,9 +5,10 @@
 // pair sp_matmul_topn products (:737-743), the zip over right blocks (:746)
 // and the vstack over left blocks (:750).  See DESIGN.md §K2 for the layout.
 //
-//   postings_build   right matrix  -> (feature, column-tile) bucketed postings
-//   candidates       Gustavson row-wise product, fp32, shared-memory accumulator
-//                    tile per warp, emits (row, col) with score > thr - margin
+//   postings_build   right matrix  -> (feature, column-tile) bucketed postings + directory with block maxima
+//   candidates       block-max test of 64 tiles at a time, then the Gustavson row-wise product of the pruned left
+//                    row over the surviving tiles into a shared-memory accumulator tile per warp (16-bit fixed
+//                    point or fp32); emits (row, col) with partial score > the (row, tile) candidate threshold
 //   rescore          exact sorted-merge dot product of every candidate pair
 //   topn_select      strict threshold, top-n per row, value-descending
 #include <cub/cub.cuh>
@@ -18,7 +19,7 @@
 namespace sg {
 
 // ---------------------------------------------------------------------------
-// postings build: tile-major, column-sorted, in signature order of the right rows
+// postings build: feature-major buckets (feature, column tile), column-sorted, in the processing order of the right rows
 // ---------------------------------------------------------------------------
 // key = (bucket << 16) | local column; bucket = f * T + t (feature-major: the buckets a left row walks for one of its
 // features over consecutive column tiles are neighbours in the directory and in the posting array), t = rank[doc] / tile_w
