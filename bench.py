@@ -381,6 +381,7 @@ def main():
                 "walked": {"macs": walked, "share_of_full": (walked / macs_local) if walked else None,
                            "posting_bytes": 4 * walked if walked else None,
                            "posting_GBps": (4 * walked / (k2_ms / 1e3) / 1e9) if walked else None,
+                           "posting_frac_of_peak": (4 * walked / (k2_ms / 1e3) / 1e9 / peak) if walked else None,
                            "prune": st_count.get("prune"), "accumulator": st_count.get("acc")},
                 "pipe": pipe,
                 "tile": {k: info["stats"].get(k) for k in ("tile_w", "warps", "n_tiles", "n_candidates",
