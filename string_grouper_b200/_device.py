@@ -550,9 +550,10 @@ def symmetrize(M, fix_diagonal=True, mirror=True):
     return DeviceMatches(M.shape, out_row, out_col, out_score, nnz, M.max_row, out_dtype=M.out_dtype)
 
 
-def group_reps(M, n, centroid):
+def group_reps(M, n, centroid, keep_device=False):
     """Representative index of every string's group from the (row, col)-sorted device match list
-    (StringGrouper._deduplicate, string_grouper.py:851-904)."""
+    (StringGrouper._deduplicate, string_grouper.py:851-904).  keep_device: also return the int32 device tensor
+    (positions for the device string gather)."""
     t = require_cuda()
     L = _lib.load()
     dev = M.d_row.device
@@ -562,7 +563,8 @@ def group_reps(M, n, centroid):
     _lib.check(L.sg_group_reps(n, M.nnz, _ptr(M.d_row), _ptr(M.d_col), _ptr(M.d_score), 1 if centroid else 0,
                                _ptr(rep), _ptr(ws), ws_bytes, _stream()))
     LAUNCH_COUNTS["groups"] += 6
-    return rep[:n].cpu().numpy().astype(np.int64)
+    host = rep[:n].cpu().numpy().astype(np.int64)
+    return (host, rep) if keep_device else host
 
 
 def nearest_master(M, n_right):

@@ -539,9 +539,15 @@ class StringGrouper(object):
         """Connected components of the match graph, one representative per group (ref:851-904)."""
         n = len(self._master)
         centroid = self._config.group_rep == GROUP_REP_CENTROID
+        rep_values = None
         if self._matches_device is not None:
             # components, similarity sums and representatives on the device (csrc/sg_groups.cu)
-            rep = _device.group_reps(self._matches_device, n, centroid)
+            rep, d_rep = _device.group_reps(self._matches_device, n, centroid, keep_device=True)
+            raw = self._raw_device
+            if raw is not None and n > 0 and _is_arrow_str(self._master) and raw.n_master == n:
+                # the strings are in HBM too: gather the representatives there (the Series.iloc of ref:897)
+                (rhost,) = _device.gather_strings(raw, [(0, d_rep, n)])
+                rep_values = _gathered_array(self._master, *rhost)
         else:
             # the list was edited by add_match / remove_match: host statement of the same rule
             pairs = self._matches_list
@@ -562,7 +568,19 @@ class StringGrouper(object):
 
         prefix = GROUP_REP_PREFIX
         label = f'{prefix}{self._master.name}' if self._master.name else prefix[:-1]
-        output = self._master.iloc[rep].rename(label).reset_index(drop=ignore_index)
+        index = self._master.index
+        if rep_values is not None and (ignore_index or (index.nlevels == 1 and index.name is None and label != 'index')):
+            # fast path: the gathered strings become the column directly (same frame as the general path below)
+            if ignore_index:
+                output = pd.Series(rep_values, name=label, copy=False)
+            else:
+                if isinstance(index, pd.RangeIndex):
+                    labels = rep if (index.start == 0 and index.step == 1) else index.start + index.step * rep
+                else:
+                    labels = index.to_numpy()[rep]
+                output = pd.DataFrame({'index': labels, label: rep_values}, copy=False)
+        else:
+            output = self._master.iloc[rep].rename(label).reset_index(drop=ignore_index)
         if isinstance(output, pd.DataFrame):
             output.rename(columns={c: f'{prefix}{c}' for c in output.columns if str(c) != label}, inplace=True)
         if self._master_id is not None:
