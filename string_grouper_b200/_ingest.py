@@ -88,6 +88,7 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
     for s in series_list:
         data, offsets = _arrow_buffers(s)
         n = len(offsets) - 1
+        mx = None               # largest byte of `data`; None = not known (after a re-encode)
         if not default_regex:
             # host runs the whole analyzer prefix (string_grouper.py:372-376) with the user's pattern
             pat = re.compile(regex)
@@ -100,7 +101,7 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
                     x = normalize('NFKD', x).encode('ASCII', 'ignore').decode()
                 out.append(pat.sub('', x))
             data, offsets = _encode_list(out)
-        elif data.size and int(data.max()) >= 0x80:
+        elif (mx := int(data.max()) if data.size else 0) >= 0x80:
             bad = np.unique(np.searchsorted(offsets, np.nonzero(data >= 0x80)[0], side='right') - 1)
             strings = s.tolist()
             for i in bad.tolist():
@@ -112,7 +113,11 @@ def pack_strings(series_list, regex=DEFAULT_REGEX, ignore_case=True, normalize_t
                 strings[i] = x
             data, offsets = _encode_list(strings)
             pristine = False
-        if data.size and int(data.max()) >= 0x80:
+            mx = None
+        # one scan of the bytes in the common all-ASCII case: the maximum is only taken again after a re-encode
+        if mx is None:
+            mx = int(data.max()) if data.size else 0
+        if mx >= 0x80:
             raise NotImplementedError(
                 "normalize_to_ascii=False with non-ASCII characters is not supported by the device vectoriser "
                 "(n-gram keys pack 7-bit characters); see DESIGN.md 'out of scope'")
