@@ -202,6 +202,58 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len
                          unsigned long long *cand_count /*[dev] 1*/,
                          unsigned long long *row_queue /*[dev] 1*/, int warps_per_cta, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * K2, tile-centric form (csrc/sg_tiles.cu) — the default for L2-normalised non-negative matrices (K1 output).
+ * Replaces the same block loop (sg.py:734-750): the reference slices the right matrix into row blocks `Bs`
+ * (:735) and runs one sp_matmul_topn per (left block, right block) pair (:737-743); here a right block is a
+ * "column tile" of 256 rows in processing order whose inverted index (postings sorted by feature, a bitmap
+ * directory over the features present, bucket offsets) is ONE contiguous blob that the candidates kernel
+ * copies into shared memory with cp.async.bulk (TMA) and an mbarrier.  Products are integers
+ * a_q*w_q (weights in 2^-15 units, rounded to nearest: the caller adds 2^-15 per kept feature to its margin).
+ *
+ *   sg_tiles_build       right matrix -> tile_desc[T] (16 B each), blob, bucket_maxw (fp16 block maxima, same
+ *                        layout as sg_postings_build), maxima[2] = {largest blob bytes, largest posting count}
+ *   sg_tiles_pack_left   pruned left rows (sg_prune_rows) in processing order `perm` -> lpack {feature, a_q}
+ *                        at the rows' own CSR positions, rowinfo[rank] = {start, kept, threshold, pruned norm}
+ *   sg_tiles_filter      block-max test of every (left rank, tile): mask[word*mask_stride + rank], the 64 tiles
+ *                        [64b, 64b+64) in words 2b (even tiles) and 2b+1 (odd tiles), bit (tile & 63) >> 1
+ *   sg_tiles_candidates  persistent CTAs over (tile, rank segment) items from `queue` [dev, zeroed]; reports
+ *                        (row, col) in original ids; cand_count as in sg_cossim_candidates; `walk_stats`
+ *                        [dev, 2 x u64, optional]: (row, tile) pairs taken and postings added
+ * Limits: n_cols <= sg_tiles_max_cols(); one tile's blob must fit shared memory (else SG_ERR_UNSUPPORTED and
+ * the caller falls back to sg_cossim_candidates).
+ * ------------------------------------------------------------------------- */
+int sg_tiles_tile_w(void);
+int64_t sg_tiles_max_cols(void);
+int64_t sg_tiles_blob_bound(int64_t nnz, int64_t n_rows, int64_t n_cols);
+size_t sg_tiles_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int sg_tiles_build(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *indptr /*[dev]*/,
+                   const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/,
+                   const int32_t *rank /*[dev] or NULL*/, int64_t indptr_base, float w_scale,
+                   void *tile_desc /*[dev] T*16 B*/, void *blob /*[dev] blob_cap B*/, int64_t blob_cap,
+                   void *bucket_maxw /*[dev] (n_cols+1)*Tp*2 B*/, int32_t *maxima /*[dev] 2*/, void *ws /*[dev]*/,
+                   size_t ws_bytes, void *stream);
+int sg_tiles_pack_left(int64_t n_ranks, const int32_t *perm /*[dev] or NULL*/, int64_t row_begin,
+                       const int64_t *indptr /*[dev]*/, const int32_t *pruned_len /*[dev] per row id or NULL*/,
+                       const int32_t *pruned_indices /*[dev]*/, const float *pruned_val32 /*[dev]*/,
+                       const float *threshold_row /*[dev] per row id*/,
+                       const float *pruned_norm_row /*[dev] per row id or NULL*/, float a_scale,
+                       void *lpack /*[dev] 8 B per stored value*/, void *rowinfo /*[dev] 16 B per rank*/,
+                       void *stream);
+int64_t sg_tiles_mask_words(int64_t n_right);
+int sg_tiles_filter(int64_t n_ranks, const void *rowinfo /*[dev]*/, const void *lpack /*[dev]*/,
+                    const void *bucket_maxw /*[dev]*/, int64_t n_right, const float *tile_bound /*[dev]*/,
+                    uint32_t *mask /*[dev] words*mask_stride*/, int64_t mask_stride, void *stream);
+size_t sg_tiles_smem_bytes(int stage_bytes, int warps_per_cta);
+int sg_tiles_candidates(const int32_t *perm_a /*[dev] or NULL*/, int64_t n_ranks, int64_t row_begin,
+                        const void *rowinfo /*[dev]*/, const void *lpack /*[dev]*/, const uint32_t *mask /*[dev]*/,
+                        int64_t mask_stride, const void *tile_desc /*[dev]*/, const void *blob /*[dev]*/,
+                        int64_t n_right, int64_t n_cols, const float *tile_bound /*[dev]*/,
+                        const int32_t *perm_b /*[dev] or NULL*/, int stage_bytes /* maxima[0] */,
+                        int32_t *cand_row /*[dev] cap*/, int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
+                        unsigned long long *cand_count /*[dev] 1*/, unsigned long long *queue /*[dev] 1*/,
+                        unsigned long long *walk_stats /*[dev] 2 or NULL*/, int warps_per_cta, void *stream);
+
 /*
  * Exact re-scoring of the candidates: sorted-merge dot product of left row i
  * and right row j in ascending feature order (the accumulation order of

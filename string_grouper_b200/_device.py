@@ -15,6 +15,7 @@ _TORCH = None
 # hand-written kernels launched so far (CUB scans / sorts and memsets are not counted); bench.py "gpu_launches"
 LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "symmetrize": 0, "tfidf": 0,
                  "rowdot": 0, "order": 0, "tiles": 0, "groups": 0, "gather": 0, "prune": 0}
+# "tiles": the tile-centric K2 (csrc/sg_tiles.cu): build, pack_left, filter, candidates
 
 TRANSFER_BYTES = {"d2h": 0, "h2d": 0}      # bytes moved by the bulk copies (bench.py e2e accounting)
 
@@ -30,6 +31,13 @@ ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulato
 MAX_CAND_DENSITY = float(os.environ.get("SG_B200_MAX_CAND_DENSITY", "1.5e-3"))   # candidates per (row, column) pair
 MAX_BUCKETS = int(os.environ.get("SG_B200_MAX_BUCKETS", str(400_000_000)))       # directory entries (22 B each)
 CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
+# K2 formulation for L2-normalised non-negative operands: "tiles" = right tiles staged through TMA into shared memory
+# (csrc/sg_tiles.cu, the default), "row" = one warp per left row over L2-resident posting buckets (csrc/sg_cossim.cu,
+# also the general path: negative values, norms above 1, near-zero thresholds)
+K2_KERNEL = os.environ.get("SG_B200_KERNEL", "tiles").lower()
+TILE_MARGIN = 2e-5               # fp32 arithmetic of thresholds / norms and the f64 -> f32 copy of the values
+TILE_MARGIN_PER_FEATURE = 3.1e-5  # a_q * w_q / 2^30 vs a * w: both weights rounded to nearest 2^-15 (<= 2^-15 + 2^-32)
+TILE_WARPS = int(os.environ.get("SG_B200_TILE_WARPS", "8"))
 
 
 def torch():
@@ -101,6 +109,7 @@ class DeviceCSR:
         self._host = None
         self._order = None          # (hrank, perm, rank): rows ordered by (quantised heavy norm, heavy-feature signature)
         self._postings2 = {}
+        self._tiles = None          # tile blobs of the tile-centric K2 (right_tiles)
         self.row_offset = None      # set when this matrix is one rank's block of rows of a sharded matrix
         self.global_rows = None
         self._df = None             # document frequency of every feature (sg_feature_df)
@@ -205,17 +214,53 @@ def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True, row_norm=None
     return perm, rank
 
 
-def right_side(B, tile_w):
-    """Row order (heavy norm, signature), feature-major column-sorted postings, bucket directory with block maxima and
-    per-tile pruning bounds of the right matrix, cached on B."""
-    t = require_cuda()
-    L = _lib.load()
+def right_order(B):
+    """(hrank, perm, rank) of the right matrix: heavy features, rows sorted by (quantised heavy norm, signature)."""
     if B._order is None:
         hrank = heavy_features(B)
         B._heavy_norm = heavy_norms(B, hrank)
         perm, rank = row_order(B, hrank, row_norm=B._heavy_norm, norm_scale=1.0 / max(B.norm_bound, 1e-30))
         B._order = (hrank, perm, rank)
-    hrank, perm, rank = B._order
+    return B._order
+
+
+def right_tiles(B):
+    """Tile blobs of the tile-centric K2 (csrc/sg_tiles.cu), cached on B: per 256-row tile of the processing order
+    the postings sorted by feature, the bitmap directory and the bucket offsets as one blob (what the candidates
+    kernel stages through TMA), the fp16 block maxima of every (feature, tile) and the per-tile pruning bound."""
+    t = require_cuda()
+    L = _lib.load()
+    hrank, perm, rank = right_order(B)
+    if B._tiles is None:
+        n_rows, n_cols = B.shape
+        W = int(L.sg_tiles_tile_w())
+        T = int(L.sg_num_tiles(n_rows, W))
+        Tp = int(L.sg_num_tiles_padded(n_rows, W))
+        cap = int(L.sg_tiles_blob_bound(B.nnz, n_rows, n_cols))
+        blob = _empty(cap, t.uint8, B.device)
+        desc = _empty(2 * T, t.int64, B.device)
+        maxw = _empty((n_cols + 1) * Tp, t.float16, B.device)
+        maxima = t.zeros(2, dtype=t.int32, device=B.device)
+        ws_bytes = int(L.sg_tiles_workspace_bytes(B.nnz, n_rows, n_cols))
+        ws = _empty(ws_bytes, t.uint8, B.device)
+        _lib.check(L.sg_tiles_build(n_rows, n_cols, B.nnz, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val32),
+                                    _ptr(rank), B.base, 1.0 / max(B.norm_bound, 1.0), _ptr(desc), _ptr(blob), cap,
+                                    _ptr(maxw), _ptr(maxima), _ptr(ws), ws_bytes, _stream()))
+        LAUNCH_COUNTS["tiles"] += 4
+        bound = t.zeros(Tp, dtype=t.float32, device=B.device)
+        _lib.check(L.sg_tile_bounds(n_rows, _ptr(perm), _ptr(B._heavy_norm), W, _ptr(bound), _stream()))
+        LAUNCH_COUNTS["prune"] += 1
+        B._tiles = {"desc": desc, "blob": blob, "maxw": maxw, "bound": bound, "maxima": maxima, "T": T, "W": W,
+                    "stage_bytes": None}
+    return B._tiles
+
+
+def right_side(B, tile_w):
+    """Row order (heavy norm, signature), feature-major column-sorted postings, bucket directory with block maxima and
+    per-tile pruning bounds of the right matrix, cached on B."""
+    t = require_cuda()
+    L = _lib.load()
+    hrank, perm, rank = right_order(B)
     if tile_w not in B._postings2:
         n_rows, n_cols = B.shape
         T = int(L.sg_num_tiles(n_rows, tile_w))
@@ -340,7 +385,7 @@ def prune_left(A, B, hrank, row_begin, row_end, threshold, margin, margin_per_fe
 
 
 def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None,
-                prune=None, acc=None):
+                prune=None, acc=None, kernel=None):
     """C[i,:] = top_n{ j : A_i . B_j > threshold } for rows [row_begin,row_end) of A.
 
     Device counterpart of the whole block loop of StringGrouper._build_matches
@@ -375,31 +420,75 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         acc = "f32"      # also near-zero thresholds: a tiny positive score must not round to a fixed-point zero
     acc_code = _lib.SG_ACC_U16 if acc == "u16" else _lib.SG_ACC_F32
     margin_pf = U16_MARGIN_PER_FEATURE if acc == "u16" else 0.0
+    # tile-centric kernel: fixed-point products need what the u16 tiles need; the bitmap directory bounds the features
+    kernel = (kernel or K2_KERNEL).lower()
+    if kernel not in ("tiles", "row"):
+        raise ValueError("kernel must be 'tiles' or 'row', got %r" % (kernel,))
+    use_tiles = kernel == "tiles" and acc == "u16" and B.shape[1] <= int(L.sg_tiles_max_cols())
+    tiles = None
+    if use_tiles:
+        tiles = right_tiles(B)
+        if tiles["stage_bytes"] is None:
+            tiles["stage_bytes"] = int(tiles["maxima"][0].item())       # one read-back per right matrix
+        smem_optin = t.cuda.get_device_properties(dev).shared_memory_per_block_optin
+        if int(L.sg_tiles_smem_bytes(tiles["stage_bytes"], TILE_WARPS)) > smem_optin:
+            use_tiles, tiles = False, None          # a tile's index does not fit shared memory: row kernel
+    if use_tiles:
+        margin = TILE_MARGIN * max(scale, 1.0)
+        margin_pf = TILE_MARGIN_PER_FEATURE
     prune_auto = prune is None          # the caller left the level open: it may be lowered, see below
     prune = PRUNE_FRAC if prune is None else float(prune)
     counters = t.zeros(4, dtype=t.int64, device=dev)       # [0] cand_count, [1] work queue
     # candidate buffer: clusters of identical names make this much larger than top_n * rows (37 M for the
     # 663k benchmark corpus); a second launch with the exact size happens only if this guess is too small
     cap = int(os.environ.get("SG_B200_CAND_CAP", 0)) or min(96 * n_rows + (1 << 22), 1 << 30)
-    tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
-    # the bucket directory holds one entry per (feature, tile): widen the tiles until it stays below MAX_BUCKETS
-    while (-(-n_right // tile_w)) * (B.shape[1] + 1) > MAX_BUCKETS and tile_w < 32768:
-        tile_w *= 2
     # both operands in the same processing order (quantised heavy norm, heavy-feature signature): neighbouring left
     # rows stream the same buckets, and the rows of a column tile have similar heavy norms (tight per-tile bound)
-    hrank, perm_b, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
+    if use_tiles:
+        hrank, perm_b, _ = right_order(B)
+        tile_w, warps, T, tile_bound = tiles["W"], TILE_WARPS, tiles["T"], tiles["bound"]
+        tiles_per_group = 0
+        lpack = _empty(2 * A.d_indices.numel(), t.int32, dev)
+        mask_words = int(L.sg_tiles_mask_words(n_right))
+    else:
+        tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
+        # the bucket directory holds one entry per (feature, tile): widen the tiles until it stays below MAX_BUCKETS
+        while (-(-n_right // tile_w)) * (B.shape[1] + 1) > MAX_BUCKETS and tile_w < 32768:
+            tile_w *= 2
+        hrank, perm_b, _, bucket_dir, bucket_maxw, post, T, tile_bound = right_side(B, tile_w)
+        # column tiles per work group (a multiple of 64): the group's posting buckets should stay L2-resident
+        tiles_per_group = max(64, int(GROUP_BYTES // max(4 * B.nnz / T, 1)) // 64 * 64)
     if A is B and row_begin == 0 and row_end == n_left:
         perm_a = perm_b
     else:
         perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
-    # column tiles per work group (a multiple of 64): the group's posting buckets should stay L2-resident
-    tiles_per_group = max(64, int(GROUP_BYTES // max(4 * B.nnz / T, 1)) // 64 * 64)
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
+    c_walk = ctypes.c_void_p(counters.data_ptr() + 16)
     dummy = _empty(1, t.int32, dev)
     pruned = {}
 
+    def launch_tiles(perm, n, row_buf, col_buf, capacity):
+        """pack the pruned rows of `perm`, block-max filter -> survivor bits, tile kernel"""
+        l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+        stride = (n + 31) // 32 * 32
+        rowinfo = _empty(4 * stride, t.int32, dev)
+        mask = _empty(mask_words * stride, t.int32, dev)
+        counters.zero_()
+        _lib.check(L.sg_tiles_pack_left(n, _ptr(perm), 0, _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val),
+                                        _ptr(l_thr), _ptr(l_xp), max(B.norm_bound, 1.0), _ptr(lpack), _ptr(rowinfo),
+                                        _stream()))
+        _lib.check(L.sg_tiles_filter(n, _ptr(rowinfo), _ptr(lpack), _ptr(tiles["maxw"]), n_right, _ptr(tile_bound),
+                                     _ptr(mask), stride, _stream()))
+        _lib.check(L.sg_tiles_candidates(_ptr(perm), n, 0, _ptr(rowinfo), _ptr(lpack), _ptr(mask), stride,
+                                         _ptr(tiles["desc"]), _ptr(tiles["blob"]), n_right, B.shape[1],
+                                         _ptr(tile_bound), _ptr(perm_b), tiles["stage_bytes"], _ptr(row_buf),
+                                         _ptr(col_buf), capacity, c_count, c_queue, c_walk, warps, _stream()))
+        LAUNCH_COUNTS["tiles"] += 3
+
     def launch(perm, rb, re_, row_buf, col_buf, capacity):
+        if use_tiles:
+            return launch_tiles(perm, re_ - rb, row_buf, col_buf, capacity)
         l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
         counters.zero_()
         _lib.check(L.sg_cossim_candidates(
@@ -439,6 +528,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
     if stats is not None:
         stats["prune"], stats["acc"] = prune, acc
+        stats["kernel"] = "tiles" if use_tiles else "row"
         stats["n_candidates_estimate"] = est
         if stats.get("count_macs") and l_len is not None:
             df = feature_df(B).long()
@@ -471,7 +561,11 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             if stats is not None and stats.get("time_kernels"):
                 ev1.record()
                 stats.setdefault("candidate_events", []).append((ev0, ev1))
-            n_cand = int(counters[0].item())
+            head = counters[:4].cpu().numpy()
+            n_cand = int(head[0])
+            if use_tiles and stats is not None:
+                stats["pairs_walked"] = stats.get("pairs_walked", 0) + int(head[2])
+                stats["postings_walked"] = stats.get("postings_walked", 0) + int(head[3])
             if n_cand <= cap:
                 break
             if n_cand * 24 > 96 * 2**30:
@@ -509,6 +603,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         stats["n_row_chunks"] = n_chunks
         stats["tile_w"], stats["warps"], stats["n_tiles"] = tile_w, warps, T
         stats["tiles_per_group"] = tiles_per_group
+        if use_tiles:
+            stats["stage_bytes"] = tiles["stage_bytes"]
 
     out_indptr = _empty(n_rows + 1, t.int64, dev)
     out_row = _empty(n_cand, t.int32, dev)

@@ -52,6 +52,17 @@ SIGNATURES = {
     "sg_tile_bounds": (_i32, [_i64, _p, _p, _i32, _p, _p]),
     "sg_cossim_candidates": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _f32,
                                     _f32, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _i32, _p]),
+    "sg_tiles_tile_w": (_i32, []),
+    "sg_tiles_max_cols": (_i64, []),
+    "sg_tiles_blob_bound": (_i64, [_i64, _i64, _i64]),
+    "sg_tiles_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "sg_tiles_build": (_i32, [_i64, _i64, _i64, _p, _p, _p, _p, _i64, _f32, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "sg_tiles_pack_left": (_i32, [_i64, _p, _i64, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p]),
+    "sg_tiles_mask_words": (_i64, [_i64]),
+    "sg_tiles_filter": (_i32, [_i64, _p, _p, _p, _i64, _p, _p, _i64, _p]),
+    "sg_tiles_smem_bytes": (_sz, [_i32, _i32]),
+    "sg_tiles_candidates": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _p, _p, _i32, _p, _p, _i64,
+                                   _p, _p, _p, _i32, _p]),
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _sz, _p]),

@@ -14,14 +14,16 @@ def _oracle():
     return pipeline
 
 
-def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, prune=None, acc=None, stats=None):
+def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, prune=None, acc=None, stats=None,
+         kernel=None):
     from string_grouper_b200 import _device as D
     P = _oracle()
     m, d, _ = P.tf_idf_matrices(master, dupes, dtype=dtype)
     ref = P.build_matches(m, d, None, top_n, thr, n_threads=4)
     A = D.DeviceCSR.from_scipy(m)
     B = A if dupes is None else D.DeviceCSR.from_scipy(d)
-    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps, prune=prune, acc=acc, stats=stats)
+    got = D.cossim_topn(A, B, top_n, thr, tile_w=tile_w, warps=warps, prune=prune, acc=acc, stats=stats,
+                        kernel=kernel)
     return m, d, ref, got
 
 
@@ -32,9 +34,14 @@ def _run(master, dupes, top_n, thr, dtype=np.float64, tile_w=None, warps=None, p
     (3000, 1, 0.5, np.float64),
     (20000, 20, 0.8, np.float64),
 ])
-def test_self_match_matches_oracle(n, top_n, thr, dtype):
+@pytest.mark.parametrize("kernel", ["tiles", "row"])
+def test_self_match_matches_oracle(n, top_n, thr, dtype, kernel):
     names = make_names(n, seed=1)
-    m, d, ref, got = _run(names, None, top_n, thr, dtype)
+    st = {}
+    m, d, ref, got = _run(names, None, top_n, thr, dtype, kernel=kernel, stats=st)
+    assert st["kernel"] == kernel          # the TMA-staged tile kernel is the default path for K1 output
+    if kernel == "tiles":
+        assert st["postings_walked"] > 0 and st["pairs_walked"] > 0
     gr, gc, gs = got.host_triples()
     cut = row_cutoffs(ref.indptr, ref.data, top_n, n)
     st = compare_triples(csr_triples(ref), (gr, gc, gs), n, thr, cutoff_row=cut, label="self %d" % n)
@@ -54,7 +61,7 @@ def test_two_series_and_tilings_agree():
     compare_triples(csr_triples(ref), got.host_triples(), len(dupes), 0.7, cutoff_row=cut, label="two-series")
     # block invariance (reference tests test_n_blocks_*): any tile shape gives the same answer
     for tile_w, warps in [(128, 4), (256, 8), (1024, 16), (3072, 16), (1536, 32)]:
-        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps)
+        _, _, _, g2 = _run(master, dupes, 20, 0.7, tile_w=tile_w, warps=warps, kernel="row")
         a, b = got.host_triples(), g2.host_triples()
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
@@ -66,20 +73,25 @@ def test_pruning_and_accumulator_variants_agree(thr):
     fp32 traversal, and those equal the oracle."""
     names = make_names(12000, seed=11)
     st0 = {"count_macs": True}
-    m, d, ref, base = _run(names, None, 20, thr, prune=0.0, acc="f32", stats=st0)
+    m, d, ref, base = _run(names, None, 20, thr, prune=0.0, acc="f32", stats=st0, kernel="row")
     cut = row_cutoffs(ref.indptr, ref.data, 20, len(names))
     compare_triples(csr_triples(ref), base.host_triples(), len(names), thr, cutoff_row=cut, label="unpruned")
     b = base.host_triples()
     walked = {}
-    for prune, acc, tile_w in [(0.0, "u16", None), (0.5, "f32", None), (0.7, "u16", None), (0.9, "f32", 256),
-                               (0.95, "u16", 512), (0.7, "u16", 3072)]:
+    for prune, acc, tile_w, kernel in [(0.0, "u16", None, "row"), (0.5, "f32", None, "row"), (0.7, "u16", None, "row"),
+                                       (0.9, "f32", 256, "row"), (0.95, "u16", 512, "row"), (0.7, "u16", 3072, "row"),
+                                       (0.0, "u16", None, "tiles"), (0.5, "u16", None, "tiles"),
+                                       (0.9, "u16", None, "tiles"), (0.97, "u16", None, "tiles")]:
         st = {"count_macs": True}
-        _, _, _, got = _run(names, None, 20, thr, prune=prune, acc=acc, tile_w=tile_w, stats=st)
+        _, _, _, got = _run(names, None, 20, thr, prune=prune, acc=acc, tile_w=tile_w, stats=st, kernel=kernel)
         g = got.host_triples()
-        assert got.nnz == base.nnz, (prune, acc, got.nnz, base.nnz)
+        assert got.nnz == base.nnz, (prune, acc, kernel, got.nnz, base.nnz)
         for x, y in zip(b, g):
-            assert np.array_equal(x, y), (prune, acc, tile_w)
-        walked[(prune, acc)] = st.get("macs_walked")
+            assert np.array_equal(x, y), (prune, acc, tile_w, kernel)
+        if kernel == "row":
+            walked[(prune, acc)] = st.get("macs_walked")
+        else:
+            assert st["kernel"] == "tiles" or thr - 1e-3 < 0.05
     full = walked[(0.0, "u16")]
     assert walked[(0.7, "u16")] < 0.6 * full and walked[(0.95, "u16")] <= walked[(0.7, "u16")]
 
@@ -116,16 +128,17 @@ def test_row_chunks_and_adaptive_pruning_level(monkeypatch):
     A = D.DeviceCSR.from_scipy(m)
     base = D.cossim_topn(A, A, 20, 0.8, prune=0.0, acc="f32")
     b = base.host_triples()
-    st = {}
     monkeypatch.setattr(D, "CAND_CHUNK", 1 << 19)
-    got = D.cossim_topn(A, A, 20, 0.8, stats=st)
-    assert st["n_row_chunks"] > 1
-    for x, y in zip(b, got.host_triples()):
-        assert np.array_equal(x, y)
-    # a bucket directory that would exceed MAX_BUCKETS entries makes the tiles wider
+    for kernel in ("tiles", "row"):
+        st = {}
+        got = D.cossim_topn(A, A, 20, 0.8, stats=st, kernel=kernel)
+        assert st["n_row_chunks"] > 1 and st["kernel"] == kernel
+        for x, y in zip(b, got.host_triples()):
+            assert np.array_equal(x, y)
+    # a bucket directory that would exceed MAX_BUCKETS entries makes the tiles of the row kernel wider
     st3 = {}
     monkeypatch.setattr(D, "MAX_BUCKETS", 2_000_000)
-    got3 = D.cossim_topn(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(m), 20, 0.8, stats=st3)
+    got3 = D.cossim_topn(D.DeviceCSR.from_scipy(m), D.DeviceCSR.from_scipy(m), 20, 0.8, stats=st3, kernel="row")
     assert st3["tile_w"] > st["tile_w"]
     for x, y in zip(b, got3.host_triples()):
         assert np.array_equal(x, y)
