@@ -84,6 +84,40 @@ def matches_list(matches):
                          'similarity': matches.data})
 
 
+def get_matches_frame(master, ml, duplicates=None, ignore_index=False):
+    """:443-518 for the id-less case — strings (and index columns) gathered by position, prefixed, concatenated."""
+    left = master if master.name else master.rename('side')
+    left = left.iloc[ml.master_side].reset_index(drop=ignore_index)
+    right = master if duplicates is None else duplicates
+    right = right if right.name else right.rename('side')
+    right = right.iloc[ml.dupe_side].reset_index(drop=ignore_index)
+    right = right if isinstance(right, pd.Series) else right[right.columns[::-1]]
+
+    def prefixed(data, prefix):
+        if isinstance(data, pd.DataFrame):
+            return data.rename(columns={c: f"{prefix}{c}" for c in data.columns})
+        return data.rename(f"{prefix}{data.name}")
+
+    return pd.concat([prefixed(left, 'left_'), ml.similarity.reset_index(drop=True), prefixed(right, 'right_')], axis=1)
+
+
+def deduplicate(ml, n, group_rep='centroid'):
+    """:851-904 — index of every string's group representative: weakly connected components of the match
+    graph (:863), weight = row index ('first') or row sum of similarities ('centroid', :875-881), representative =
+    groupby(...).transform('first' | 'idxmax') (:885-886)."""
+    from scipy.sparse.csgraph import connected_components
+    graph = csr_matrix((np.full(len(ml), 1), (ml.master_side.to_numpy(), ml.dupe_side.to_numpy())), shape=(n, n))
+    _, groups = connected_components(csgraph=graph, directed=True)
+    g = pd.Series(groups, name='raw_group_id').reset_index()
+    g.rename(columns={'index': 'weight'}, inplace=True)
+    method = 'first'
+    if group_rep == 'centroid':
+        graph.data = ml['similarity'].to_numpy()
+        g['weight'] = pd.Series(np.asarray(graph.sum(axis=1)).squeeze(axis=1))
+        method = 'idxmax'
+    return g.groupby('raw_group_id', sort=False)['weight'].transform(method).to_numpy().astype(np.int64)
+
+
 def fit(master, duplicates=None, *, ngram_size=3, regex=DEFAULT_REGEX, ignore_case=True,
         normalize_to_ascii=True, tfidf_matrix_dtype=np.float64, max_n_matches=20,
         min_similarity=0.8, n_blocks=None, force_symmetries=True, n_threads=1,

@@ -69,6 +69,24 @@ def _empty(n, dtype, device):
     return torch().empty(max(int(n), 1), dtype=dtype, device=device)
 
 
+def mark(stats, name):
+    """Phase boundary for bench.py `phases_ms`: a CUDA event on the current stream when stats["time_kernels"] is set."""
+    if stats is not None and stats.get("time_kernels"):
+        ev = torch().cuda.Event(enable_timing=True)
+        ev.record()
+        stats.setdefault("marks", []).append((name, ev))
+
+
+def phases_ms(stats):
+    """{phase: milliseconds} from the marks of one step (the time between a mark and its predecessor is charged to
+    the mark's name; the first mark only starts the clock)."""
+    out = {}
+    marks = stats.get("marks", [])
+    for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+    return out
+
+
 def to_host(*tensors):
     """Device tensors -> numpy arrays through page-locked staging buffers (torch's caching host allocator
     re-uses them from call to call): all copies are queued on the current stream, one synchronisation.
@@ -409,6 +427,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         z32 = _empty(1, t.int32, dev)
         return DeviceMatches(shape, z32, z32, _empty(1, t.float64, dev), 0, 0)
 
+    mark(stats, "k2_start")
     scale = A.norm_bound * B.norm_bound
     margin = CAND_MARGIN * max(scale, 1.0)
     thr_c = max(float(threshold) - margin, 0.0)
@@ -462,6 +481,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         perm_a = perm_b
     else:
         perm_a, _ = row_order(A, hrank, row_begin, row_end, want_rank=False)
+    mark(stats, "right_side")
     c_count = ctypes.c_void_p(counters.data_ptr())
     c_queue = ctypes.c_void_p(counters.data_ptr() + 8)
     c_walk = ctypes.c_void_p(counters.data_ptr() + 16)
@@ -526,6 +546,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         if est <= MAX_CAND_DENSITY * n_rows * n_right:
             break
     l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+    mark(stats, "prune_sample")
     if stats is not None:
         stats["prune"], stats["acc"] = prune, acc
         stats["kernel"] = "tiles" if use_tiles else "row"
@@ -575,6 +596,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         else:
             raise OverflowError("candidate buffer overflow")
         n_cand_total += n_cand
+        mark(stats, "candidates")
         # exact scores; only the candidates strictly above the threshold go on to the selection sorts
         score = _empty(n_cand, t.float64, dev)
         keep_row = _empty(n_cand, t.int32, dev)
@@ -585,6 +607,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                 float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _stream()))
         LAUNCH_COUNTS["rescore"] += 1
         n_keep = int(counters[0].item())
+        mark(stats, "rescore")
         if n_chunks > 1:      # release the chunk-sized buffers, keep the survivors
             keep_row, keep_col, score = keep_row[:n_keep].clone(), keep_col[:n_keep].clone(), score[:n_keep].clone()
         kept.append((keep_row, keep_col, score, n_keep))
@@ -619,6 +642,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                 ws_bytes, _stream()))
     LAUNCH_COUNTS["select"] += 7
     th = tail.cpu().numpy()
+    mark(stats, "select")
     nnz = int(th[0])
     max_row = int(th[1:2].view(np.int32)[0])
     return DeviceMatches(shape, out_row, out_col, out_score, nnz, max_row, indptr=out_indptr)

@@ -43,7 +43,7 @@ constexpr int TL_W = 256;            // columns per tile (accumulator: 256 x u32
 constexpr int TL_CBUF = 96;          // candidate buffer entries per warp
 constexpr float TL_FIX = 32768.f;    // weights in 2^-15 units, products in 2^-30 units
 constexpr int TL_WARP_BYTES = TL_W * 4 + 64 * 4 + 32 * 8 + TL_CBUF * 8;
-constexpr int TL_HEAD_BYTES = 128;   // mbarrier, item broadcast, chunk counter
+constexpr int TL_HEAD_BYTES = 128;   // mbarrier, item broadcast, survivor count
 
 __host__ __device__ __forceinline__ int a16(int x) { return (x + 15) & ~15; }
 // bitmap words per tile: one bit per feature, rounded up to 16 bytes
@@ -328,7 +328,7 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
 // ---------------------------------------------------------------------------
 // candidates
 // ---------------------------------------------------------------------------
-constexpr int tl_min_ctas(int nw) { return nw == 16 ? 2 : 4; }
+constexpr int tl_min_ctas(int nw) { return nw == 16 ? 1 : 3; }
 
 struct WarpCtx {
     uint32_t *acc;          // TL_W partial scores, 2^-30 units
@@ -371,6 +371,109 @@ __device__ __forceinline__ void flush_candidates(WarpCtx &cx, int lane, const in
         }                                                                                                 \
     } while (0)
 
+// One (left row, tile) pair: buckets of the row's kept features through the bitmap directory, long buckets streamed
+// by the warp, all others walked as one concatenated list; columns whose partial score crosses the threshold are
+// buffered as candidates.
+#define TL_PAIR(rank_id_, info_, fa_first_)                                                                         \
+    do {                                                                                                            \
+        const int rank_id = (rank_id_);                                                                             \
+        const int cur_p0 = (info_).x, cur_nf = (info_).y;                                                           \
+        const float thr_r = __int_as_float((info_).z);                                                              \
+        const float xp = __int_as_float((info_).w);                                                                 \
+        const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;                                \
+        const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));                   \
+        bool touched = false;                                                                                       \
+        ++n_pairs;                                                                                                  \
+        for (int fb = 0; fb < cur_nf; fb += 32) {                                                                   \
+            int2 e_fa = (fa_first_);                                                                                \
+            if (fb > 0) {                                                                                           \
+                e_fa = make_int2(0, 0);                                                                             \
+                if (fb + lane < cur_nf) e_fa = lpack[(int64_t)cur_p0 + fb + lane];                                  \
+            }                                                                                                       \
+            int len = 0, o0 = 0;                                                                                    \
+            if (fb + lane < cur_nf) {                                                                               \
+                const unsigned f = (unsigned)e_fa.x;                                                                \
+                const uint32_t bmw = bitmap[f >> 5];                                                                \
+                if ((bmw >> (f & 31)) & 1u) {                                                                       \
+                    const int jb = (int)prefix[f >> 5] + __popc(bmw & ((1u << (f & 31)) - 1u));                     \
+                    o0 = off[jb];                                                                                   \
+                    len = (int)off[jb + 1] - o0;                                                                    \
+                }                                                                                                   \
+            }                                                                                                       \
+            const unsigned aq = (unsigned)e_fa.y;                                                                   \
+            unsigned lm = __ballot_sync(FULL, len >= TL_LONG);                                                      \
+            while (lm) {                                                                                            \
+                const int s_ = __ffs(lm) - 1;                                                                       \
+                lm &= lm - 1;                                                                                       \
+                const int b0 = __shfl_sync(FULL, o0, s_);                                                           \
+                const int b1 = b0 + __shfl_sync(FULL, len, s_);                                                     \
+                const unsigned ak = __shfl_sync(FULL, aq, s_);                                                      \
+                n_walked += (unsigned)(b1 - b0);                                                                    \
+                for (int p = b0; p < b1; p += 32) {                                                                 \
+                    bool crossed = false;                                                                           \
+                    unsigned cb = 0;                                                                                \
+                    if (p + lane < b1) {                                                                            \
+                        const uint32_t e = post[p + lane];                                                          \
+                        const unsigned x = (e >> 16) * ak;                                                          \
+                        cb = e & 0xffffu;                                                                           \
+                        const unsigned old = atomicAdd(                                                             \
+                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
+                        crossed = old <= thr_c && old + x > thr_c;                                                  \
+                    }                                                                                               \
+                    TL_EMIT(crossed, cb);                                                                           \
+                }                                                                                                   \
+                touched = true;                                                                                     \
+            }                                                                                                       \
+            const int ln = len >= TL_LONG ? 0 : len;                                                                \
+            int incl = ln;                                                                                          \
+            _Pragma("unroll") for (int o = 1; o < 32; o <<= 1) {                                                    \
+                const int up = __shfl_up_sync(FULL, incl, o);                                                       \
+                if (lane >= o) incl += up;                                                                          \
+            }                                                                                                       \
+            const int total = __shfl_sync(FULL, incl, 31);                                                          \
+            if (total > 0) {                                                                                        \
+                touched = true;                                                                                     \
+                n_walked += (unsigned)total;                                                                        \
+                const unsigned nz = __ballot_sync(FULL, ln > 0);                                                    \
+                if (ln > 0) {                                                                                       \
+                    const int st = incl - ln;                                                                       \
+                    cx.dk[__popc(nz & lt_mask)] = make_int2(o0 - st, (int)aq);                                      \
+                    atomicOr(&cx.flags[st >> 5], 1u << (st & 31));                                                  \
+                }                                                                                                   \
+                __syncwarp();                                                                                       \
+                int kbase = -1;                                                                                     \
+                for (int s0 = 0; s0 < total; s0 += 32) {                                                            \
+                    const uint32_t fw = cx.flags[s0 >> 5];                                                          \
+                    const int k = kbase + __popc(fw & le_mask);                                                     \
+                    kbase += __popc(fw);                                                                            \
+                    __syncwarp();                                                                                   \
+                    if (lane == 0) cx.flags[s0 >> 5] = 0u;                                                          \
+                    bool crossed = false;                                                                           \
+                    unsigned cb = 0;                                                                                \
+                    if (s0 + lane < total) {                                                                        \
+                        const int2 dd = cx.dk[k];                                                                   \
+                        const uint32_t e = post[dd.x + s0 + lane];                                                  \
+                        const unsigned x = (e >> 16) * (unsigned)dd.y;                                              \
+                        cb = e & 0xffffu;                                                                           \
+                        const unsigned old = atomicAdd(                                                             \
+                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
+                        crossed = old <= thr_c && old + x > thr_c;                                                  \
+                    }                                                                                               \
+                    TL_EMIT(crossed, cb);                                                                           \
+                }                                                                                                   \
+                __syncwarp();                                                                                       \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (touched) {                                                                                              \
+            __syncwarp();                                                                                           \
+            _Pragma("unroll") for (int c = 0; c < TL_W * 4 / 16 / 32; ++c)                                          \
+                reinterpret_cast<uint4 *>(cx.acc)[c * 32 + lane] = zero4;                                           \
+            __syncwarp();                                                                                           \
+        }                                                                                                           \
+    } while (0)
+
+__host__ __device__ constexpr int tl_list(int nw) { return nw * 256; }     // survivor ranks per scan round (every warp scans 256 ranks)
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, tl_min_ctas(NW))
 tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int64_t row_begin,
@@ -385,8 +488,9 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     volatile long long *s_item = reinterpret_cast<volatile long long *>(smem + 16);
-    int *s_chunk = reinterpret_cast<int *>(smem + 32);
-    unsigned char *stage = smem + TL_HEAD_BYTES;
+    int *s_count = reinterpret_cast<int *>(smem + 32);
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + TL_HEAD_BYTES);
+    unsigned char *stage = smem + TL_HEAD_BYTES + tl_list(NW) * 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     unsigned char *wa = stage + stage_bytes + (size_t)warp * TL_WARP_BYTES;
@@ -398,7 +502,10 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
     cx.ccount = 0;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int c = lane; c < (TL_W * 4 + 64 * 4) / 16; c += 32) reinterpret_cast<uint4 *>(wa)[c] = zero4;
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        *s_count = 0;
+    }
     __syncthreads();
 
     const unsigned long long n_items = (unsigned long long)T * (unsigned long long)n_seg;
@@ -409,13 +516,11 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         if (threadIdx.x == 0) {
             const unsigned long long it = atomicAdd(queue, 1ull);
             *s_item = (long long)it;
-            *s_chunk = 0;
             if (it < n_items) {
                 const TileDesc d = tdesc[it / (unsigned long long)n_seg];
                 const unsigned bytes = (unsigned)blob_bytes(d.n_post, d.n_dist, bw);
                 mbar_expect_tx(mbar, bytes);
-                // pieces of at most 32 KB
-                for (unsigned o = 0; o < bytes; o += 32768u) {
+                for (unsigned o = 0; o < bytes; o += 32768u) {      // pieces of at most 32 KB
                     const unsigned n = bytes - o < 32768u ? bytes - o : 32768u;
                     bulk_g2s(stage + o, blob + d.blob_off + o, n, mbar);
                 }
@@ -436,19 +541,15 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         const int col0 = t * TL_W;
         const int64_t rank_lo = seg * seg_ranks;
         const int64_t rank_hi = rank_lo + seg_ranks < n_ranks ? rank_lo + seg_ranks : n_ranks;
-        const int n_groups = (int)((rank_hi - rank_lo + 255) >> 8);
         const uint32_t *mrow = mask + (int64_t)(((t >> 6) << 1) | (t & 1)) * mask_stride;
         const int bit = (t & 63) >> 1;
-        mbar_wait(mbar, parity);
-        parity ^= 1u;
+        bool staged = false;
 
-        for (;;) {
-            int g = 0;
-            if (lane == 0) g = atomicAdd(s_chunk, 1);
-            g = __shfl_sync(FULL, g, 0);
-            if (g >= n_groups) break;
-            // ---- 256 ranks: eight coalesced mask words in flight
-            const int64_t gbase = rank_lo + ((int64_t)g << 8);
+        for (int64_t base = rank_lo; base < rank_hi; base += (int64_t)NW * 256) {
+            // ---- scan round: every warp tests 256 ranks (eight coalesced mask words in flight) and appends the
+            // survivors to the CTA's list.  Survivors cluster in rank order (similar rows are neighbours), so the list
+            // is dealt out to the warps round-robin afterwards.
+            const int64_t gbase = base + ((int64_t)warp << 8);
             uint32_t wsv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -457,134 +558,58 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
-                if (!sv) continue;
-                const int64_t cbase = gbase + j * 32;
-                int4 info = make_int4(0, 0, 0, 0);
-                if ((sv >> lane) & 1u) info = rowinfo[cbase + lane];
-                // ---- survivors of the chunk, the features of the next one fetched ahead
-                int src = __ffs(sv) - 1;
-                sv &= sv - 1;
-                int p0 = __shfl_sync(FULL, info.x, src);
-                int nf = __shfl_sync(FULL, info.y, src);
-                int2 fa = make_int2(0, 0);
-                if (lane < nf) fa = lpack[(int64_t)p0 + lane];
-                for (;;) {
-                    const int cur = src, cur_p0 = p0, cur_nf = nf;
-                    const int2 cur_fa = fa;
-                    if (sv) {
-                        src = __ffs(sv) - 1;
-                        sv &= sv - 1;
-                        p0 = __shfl_sync(FULL, info.x, src);
-                        nf = __shfl_sync(FULL, info.y, src);
-                        fa = make_int2(0, 0);
-                        if (lane < nf) fa = lpack[(int64_t)p0 + lane];
-                    } else {
-                        src = -1;
-                    }
-                    // ---- one (left row, tile) pair
-                    const float thr_r = __int_as_float(__shfl_sync(FULL, info.z, cur));
-                    const float xp = __int_as_float(__shfl_sync(FULL, info.w, cur));
-                    const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;
-                    const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));
-                    const int rank_id = (int)(cbase + cur);
-                    bool touched = false;
-                    ++n_pairs;
-                    for (int fb = 0; fb < cur_nf; fb += 32) {
-                        int2 e_fa = cur_fa;
-                        if (fb > 0) {
-                            e_fa = make_int2(0, 0);
-                            if (fb + lane < cur_nf) e_fa = lpack[(int64_t)cur_p0 + fb + lane];
-                        }
-                        // bucket of the lane's feature through the bitmap and its rank table
-                        int len = 0, o0 = 0;
-                        if (fb + lane < cur_nf) {
-                            const unsigned f = (unsigned)e_fa.x;
-                            const uint32_t bmw = bitmap[f >> 5];
-                            if ((bmw >> (f & 31)) & 1u) {
-                                const int jb = (int)prefix[f >> 5] + __popc(bmw & ((1u << (f & 31)) - 1u));
-                                o0 = off[jb];
-                                len = (int)off[jb + 1] - o0;
-                            }
-                        }
-                        const unsigned aq = (unsigned)e_fa.y;
-                        // long buckets: the whole warp streams one bucket at a time (distinct columns inside a bucket)
-                        unsigned lm = __ballot_sync(FULL, len >= TL_LONG);
-                        while (lm) {
-                            const int s = __ffs(lm) - 1;
-                            lm &= lm - 1;
-                            const int b0 = __shfl_sync(FULL, o0, s);
-                            const int b1 = b0 + __shfl_sync(FULL, len, s);
-                            const unsigned ak = __shfl_sync(FULL, aq, s);
-                            n_walked += (unsigned)(b1 - b0);
-                            for (int p = b0; p < b1; p += 32) {
-                                bool crossed = false;
-                                unsigned cb = 0;
-                                if (p + lane < b1) {
-                                    const uint32_t e = post[p + lane];
-                                    const unsigned x = (e >> 16) * ak;
-                                    cb = e & 0xffffu;
-                                    const unsigned old = atomicAdd(
-                                        reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);
-                                    crossed = old <= thr_c && old + x > thr_c;
-                                }
-                                TL_EMIT(crossed, cb);
-                            }
-                            touched = true;
-                        }
-                        // every other bucket: ONE concatenated list, 32 postings per step; the owner of a position
-                        // is the number of bucket starts at or before it (start bits + popc)
-                        const int ln = len >= TL_LONG ? 0 : len;
-                        int incl = ln;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int up = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += up;
-                        }
-                        const int total = __shfl_sync(FULL, incl, 31);
-                        if (total > 0) {
-                            touched = true;
-                            n_walked += (unsigned)total;
-                            const unsigned nz = __ballot_sync(FULL, ln > 0);
-                            if (ln > 0) {
-                                const int st = incl - ln;
-                                cx.dk[__popc(nz & lt_mask)] = make_int2(o0 - st, (int)aq);
-                                atomicOr(&cx.flags[st >> 5], 1u << (st & 31));
-                            }
-                            __syncwarp();
-                            int kbase = -1;
-                            for (int s0 = 0; s0 < total; s0 += 32) {
-                                const uint32_t fw = cx.flags[s0 >> 5];
-                                const int k = kbase + __popc(fw & le_mask);
-                                kbase += __popc(fw);
-                                __syncwarp();
-                                if (lane == 0) cx.flags[s0 >> 5] = 0u;
-                                bool crossed = false;
-                                unsigned cb = 0;
-                                if (s0 + lane < total) {
-                                    const int2 dd = cx.dk[k];
-                                    const uint32_t e = post[dd.x + s0 + lane];
-                                    const unsigned x = (e >> 16) * (unsigned)dd.y;
-                                    cb = e & 0xffffu;
-                                    const unsigned old = atomicAdd(
-                                        reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);
-                                    crossed = old <= thr_c && old + x > thr_c;
-                                }
-                                TL_EMIT(crossed, cb);
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    if (touched) {
-                        __syncwarp();
-#pragma unroll
-                        for (int c = 0; c < TL_W * 4 / 16 / 32; ++c) reinterpret_cast<uint4 *>(cx.acc)[c * 32 + lane] = zero4;
-                        __syncwarp();
-                    }
-                    if (src < 0) break;
+                const unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
+                if (sv) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(s_count, __popc(sv));
+                    pos = __shfl_sync(FULL, pos, 0);
+                    if ((sv >> lane) & 1u) s_list[pos + __popc(sv & lt_mask)] = (uint32_t)(gbase + j * 32 + lane);
                 }
             }
+            __syncthreads();
+            const int count = *reinterpret_cast<volatile int *>(s_count);
+            if (count > 0) {
+                if (!staged) {
+                    mbar_wait(mbar, parity);
+                    staged = true;
+                }
+                // ---- this warp's pairs: list entries warp, warp + NW, ...; row record two ahead, features one ahead
+                int i = warp;
+                int r_c = 0, r_n = 0;
+                int4 info_c = make_int4(0, 0, 0, 0), info_n = info_c;
+                int2 fa_c = make_int2(0, 0);
+                if (i < count) {
+                    r_c = (int)s_list[i];
+                    info_c = rowinfo[r_c];
+                }
+                if (i + NW < count) {
+                    r_n = (int)s_list[i + NW];
+                    info_n = rowinfo[r_n];
+                }
+                if (i < count && lane < info_c.y) fa_c = lpack[(int64_t)info_c.x + lane];
+                while (i < count) {
+                    int2 fa_n = make_int2(0, 0);
+                    if (i + NW < count && lane < info_n.y) fa_n = lpack[(int64_t)info_n.x + lane];
+                    int r_nn = 0;
+                    int4 info_nn = make_int4(0, 0, 0, 0);
+                    if (i + 2 * NW < count) {
+                        r_nn = (int)s_list[i + 2 * NW];
+                        info_nn = rowinfo[r_nn];
+                    }
+                    TL_PAIR(r_c, info_c, fa_c);
+                    r_c = r_n; info_c = info_n; fa_c = fa_n;
+                    r_n = r_nn; info_n = info_nn;
+                    i += NW;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) *s_count = 0;
+            // (the next round's appends come after the next __syncthreads-separated scan loads; the reset is ordered
+            // before them by the barrier below)
+            __syncthreads();
         }
+        if (!staged) mbar_wait(mbar, parity);     // nothing survived: still consume the phase before the stage is reused
+        parity ^= 1u;
         __syncthreads();      // every warp is done with the staged tile before the next one is copied over it
     }
     flush_candidates(cx, lane, perm_a, row_begin, perm_b, cand_row, cand_col, cap, cand_count);
@@ -721,7 +746,7 @@ int sg_tiles_filter(int64_t n_ranks, const void *rowinfo, const void *lpack, con
 }
 
 size_t sg_tiles_smem_bytes(int stage_bytes, int warps_per_cta) {
-    return (size_t)TL_HEAD_BYTES + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES;
+    return (size_t)TL_HEAD_BYTES + (size_t)tl_list(warps_per_cta) * 4 + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES;
 }
 
 int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begin, const void *rowinfo,

@@ -241,7 +241,11 @@ class StringGrouper(object):
         matches = _device.as_device_matches(matches)
         self._true_max_n_matches = matches.max_row
 
-        if self._config.force_symmetries and self._duplicates is None:
+        rank, world_size = _dist.world()
+        if world_size > 1 and rank != 0 and not _dist.result_on_all_ranks():
+            # SG_B200_RESULT=rank0: this rank took part in the product; the match list lives on rank 0 only
+            matches = _device.as_device_matches(csr_matrix(matches.shape, dtype=np.float64))
+        elif self._config.force_symmetries and self._duplicates is None:
             matches = StringGrouper._fix_diagonal(matches)
             matches = StringGrouper._symmetrize_matrix(matches)
             matches = _device.apply_pending(matches)
@@ -269,6 +273,9 @@ class StringGrouper(object):
         cfg = self._config
         series = [self._master] if self._duplicates is None else [self._master, self._duplicates]
         rank, world_size = _dist.world()
+        if shard and world_size > 1:
+            # sharding is opt-in (SG_B200_DISTRIBUTED); every rank must hold the same input Series
+            _dist.check_same_inputs(_dist.fingerprint(series) + [int(cfg.ngram_size), int(bool(cfg.ignore_case))])
         approx_bytes = (sum(int(s.str.len().sum()) for s in series)
                         if shard and world_size > 1 and len(series) == 2 else 0)
         stats = {}
@@ -280,7 +287,8 @@ class StringGrouper(object):
             mlo, mhi = _dist.shard_range(n_m, rank, world_size)
             dlo, dhi = _dist.shard_range(n_d, rank, world_size)
             local = [self._master.iloc[mlo:mhi], self._duplicates.iloc[dlo:dhi]]
-            data, offsets, flags, _ = _ingest.pack_strings(local, cfg.regex, cfg.ignore_case, cfg.normalize_to_ascii)
+            data, offsets, flags, _ = _dist.guarded(_ingest.pack_strings, local, cfg.regex, cfg.ignore_case,
+                                                    cfg.normalize_to_ascii)
             master, dup, vocab = _device.tfidf(data, offsets, mhi - mlo, cfg.ngram_size, flags,
                                                cfg.tfidf_matrix_dtype, stats=stats,
                                                df_allreduce=_dist.allreduce_sum_, n_docs_fit=n_m + n_d)
@@ -316,16 +324,17 @@ class StringGrouper(object):
         B = A if duplicate_matrix is master_matrix else _device.as_device_csr(duplicate_matrix)
         rank, world_size = _dist.world()
         if world_size > 1 and getattr(A, "row_offset", None) is not None:
-            # K1 was sharded: A already IS this rank's block of left rows
-            out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity,
-                                      stats=self._last_stats)
+            # K1 was sharded: A already IS this rank's block of left rows.  The rank-local product runs guarded: a
+            # rank that fails (OverflowError ...) tells the others before anybody enters the gather.
+            out = _dist.guarded(_device.cossim_topn, A, B, self._max_n_matches, self._config.min_similarity,
+                                stats=self._last_stats)
             out = _device.offset_rows(out, A.row_offset, A.global_rows)
             out = _device.gather_shards(out)
         elif world_size > 1:
             # one process per GPU: this rank computes its block of left rows, the blocks are all-gathered
             lo, hi = _dist.shard_range(A.shape[0], rank, world_size)
-            out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity, row_begin=lo,
-                                      row_end=hi, stats=self._last_stats)
+            out = _dist.guarded(_device.cossim_topn, A, B, self._max_n_matches, self._config.min_similarity,
+                                row_begin=lo, row_end=hi, stats=self._last_stats)
             out = _device.gather_shards(out)
         else:
             out = _device.cossim_topn(A, B, self._max_n_matches, self._config.min_similarity,

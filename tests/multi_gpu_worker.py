@@ -2,6 +2,7 @@
 import os
 import sys
 
+os.environ["SG_B200_DISTRIBUTED"] = "1"           # sharding is opt-in
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pandas as pd

@@ -24,6 +24,7 @@ def test_shard_ranges_follow_define_chunks():
 
 WORKER = textwrap.dedent('''
     import os, sys
+    os.environ["SG_B200_DISTRIBUTED"] = "1"       # sharding is opt-in
     sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
     import numpy as np, pandas as pd, torch.distributed as dist
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
@@ -77,3 +78,57 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path):
         pd.testing.assert_frame_equal(pd.read_pickle("%s.self.%d.pkl" % (out, r)), a)
         pd.testing.assert_frame_equal(pd.read_pickle("%s.two.%d.pkl" % (out, r)), b)
         pd.testing.assert_frame_equal(pd.read_pickle("%s.grp.%d.pkl" % (out, r)), g)
+
+
+WORKER_GUARDS = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    import pandas as pd, torch.distributed as dist
+    rank = int(sys.argv[1])
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2)
+    import string_grouper_b200 as api
+    from string_grouper_b200 import _dist
+    from cpu_backend import oracle_device
+    # 1. an initialised default group alone does not shard: rank-local data stays rank-local
+    assert _dist.world() == (0, 1)
+    local = pd.Series(["foo inc %%d" %% rank, "foo inc. %%d" %% rank, "bar llc"])
+    with oracle_device():
+        out = api.match_strings(local, min_similarity=0.5)
+    assert set(out.left_side) <= set(local)
+    # 2. opted in, but the ranks hold different Series: every rank raises instead of mixing match lists
+    _dist.enable(True)
+    assert _dist.world() == (rank, 2)
+    try:
+        with oracle_device():
+            api.match_strings(local, min_similarity=0.5)
+        raise SystemExit("expected ValueError")
+    except ValueError as e:
+        assert "different input" in str(e)
+    # 3. a rank failing in its rank-local part takes the other one down before the collective
+    def work():
+        if rank == 1:
+            raise OverflowError("boom")
+        return 7
+    try:
+        _dist.guarded(work)
+        raise SystemExit("expected an exception")
+    except OverflowError:
+        assert rank == 1
+    except RuntimeError as e:
+        assert rank == 0 and "another rank failed" in str(e)
+    # 4. SG_B200_RESULT=rank0: only rank 0 ends up with the match list
+    os.environ["SG_B200_RESULT"] = "rank0"
+    same = pd.Series(["foo inc", "foo inc.", "bar llc", "bar l.l.c"])
+    with oracle_device():
+        out = api.match_strings(same, min_similarity=0.5)
+    assert (len(out) > 0) == (rank == 0), (rank, len(out))
+    dist.destroy_process_group()
+''')
+
+
+def test_sharding_is_opt_in_and_guarded(tmp_path):
+    port = 31500 + os.getpid() % 2000
+    script = tmp_path / "worker_guards.py"
+    script.write_text(WORKER_GUARDS % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
+    assert all(p.wait(timeout=300) == 0 for p in procs)
