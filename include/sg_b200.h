@@ -286,6 +286,18 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
                    double *out_score, int64_t *out_nnz /*[dev] 1*/, int32_t *out_max_row /*[dev] 1*/,
                    void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * K3 — per-row top-n merge of column-block results.  Replaces sparse_dot_topn.zip_sp_matmul_topn(top_n, C_mats)
+ * (call site sg.py:746).  Input: the block results concatenated as COO (block column offsets already added, any
+ * order); entries that are not strictly positive are dropped like the reference's heap does (its initial minimum
+ * is the smallest positive normal of the value type `dtype`); outputs as sg_topn_select (value-descending rows).
+ */
+size_t sg_topn_merge_workspace_bytes(int64_t n_entries, int64_t n_rows);
+int sg_topn_merge(int64_t n_entries, const int32_t *row, const int32_t *col, const double *score, int64_t n_rows,
+                  int top_n, int dtype, int64_t *out_indptr, int32_t *out_row, int32_t *out_col, double *out_score,
+                  int64_t *out_nnz /*[dev] 1*/, int32_t *out_max_row /*[dev] 1*/, void *ws, size_t ws_bytes,
+                  void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Row ordering for K2 (csrc/sg_order.cu): both operands of C = A*B^T are processed in heavy-feature
  * signature order, so that the docs of a frequent n-gram are runs of consecutive column positions (the

@@ -69,6 +69,8 @@ SIGNATURES = {
     "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _p, _p]),
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sg_topn_merge_workspace_bytes": (_sz, [_i64, _i64]),
+    "sg_topn_merge": (_i32, [_i64, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_symmetrize_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_symmetrize": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_group_reps_workspace_bytes": (_sz, [_i64]),

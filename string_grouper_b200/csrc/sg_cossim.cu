@@ -859,4 +859,21 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
     return SG_OK;
 }
 
+
+// K3 — per-row top-n merge of column-block results: zip_sp_matmul_topn (string_grouper.py:746).  The block results
+// arrive concatenated as COO with block column offsets already applied; like the reference's heap (initial minimum =
+// the smallest positive normal of the value type, strict >) entries that are not strictly positive are dropped.
+size_t sg_topn_merge_workspace_bytes(int64_t n_entries, int64_t n_rows) {
+    return sg_topn_select_workspace_bytes(n_entries, n_rows);
+}
+
+int sg_topn_merge(int64_t n_entries, const int32_t *row, const int32_t *col, const double *score, int64_t n_rows,
+                  int top_n, int dtype, int64_t *out_indptr, int32_t *out_row, int32_t *out_col, double *out_score,
+                  int64_t *out_nnz, int32_t *out_max_row, void *ws, size_t ws_bytes, void *stream_) {
+    if (dtype != SG_DTYPE_F32 && dtype != SG_DTYPE_F64) return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
+    const double tiny = dtype == SG_DTYPE_F32 ? 1.17549435082228750797e-38 : 2.22507385850720138309e-308;
+    return sg_topn_select(n_entries, row, col, score, 0, n_rows, top_n, tiny, out_indptr, out_row, out_col, out_score,
+                          out_nnz, out_max_row, ws, ws_bytes, stream_);
+}
+
 }  // extern "C"

@@ -519,8 +519,16 @@ class StringGrouper(object):
         pos = np.where(hit, best, 0)
         hit_s = pd.Series(hit)
 
+        def nullable(values):
+            # masked extension dtypes (Int64, boolean ...) survive the reference's merges un-widened (ref:812-813)
+            return isinstance(values.dtype, pd.api.extensions.ExtensionDtype) and \
+                not isinstance(values.dtype, pd.StringDtype)
+
         def pick(master_series, dupe_series):
             # value of the matched master row, the duplicate's own value where nothing matched (ref:815-820)
+            if nullable(master_series):
+                taken = pd.Series(master_series.array.take(pos))
+                return taken.where(hit_s, pd.Series(dupe_series.array))
             taken = pd.Series(master_series.to_numpy()[pos])
             return taken.where(hit_s, pd.Series(dupe_series.to_numpy()))
 
@@ -530,11 +538,17 @@ class StringGrouper(object):
             d_idx = self._duplicates.index.to_frame(index=False)
             m_names = self._master.reset_index(drop=False).columns[:-1]
             for k, col in enumerate(m_names):
-                vals = pd.Series(m_idx.iloc[:, k].to_numpy()[pos]).where(hit_s, np.nan)
-                if replace_na:
-                    # ref:834-843; the dtype "restore" there assigns through .loc and therefore keeps the
-                    # NaN-widened dtype on current pandas, so none is attempted here either
-                    vals = vals.where(hit_s, pd.Series(d_idx.iloc[:, k].to_numpy()))
+                level = m_idx.iloc[:, k]
+                if nullable(level):
+                    vals = pd.Series(level.array.take(pos)).where(hit_s, pd.NA)
+                    if replace_na:
+                        vals = vals.where(hit_s, pd.Series(d_idx.iloc[:, k].array))
+                else:
+                    vals = pd.Series(level.to_numpy()[pos]).where(hit_s, np.nan)
+                    if replace_na:
+                        # ref:834-843; the dtype "restore" there assigns through .loc and therefore keeps the
+                        # NaN-widened dtype on current pandas, so none is attempted here either
+                        vals = vals.where(hit_s, pd.Series(d_idx.iloc[:, k].to_numpy()))
                 columns[f'{prefix}{col}'] = vals
         if self._master_id is not None:
             id_label = f'{prefix}{self._master_id.name if self._master_id.name else DEFAULT_MASTER_ID_NAME}'
