@@ -99,6 +99,32 @@ int sg_tfidf_vocab_keys(const int32_t *df_table /*[dev]*/, const int32_t *rank_t
                         uint32_t *keys_out /*[dev] V*/, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * K1, general form (csrc/sg_tfidf64.cu): 64-bit n-gram keys and a sort-based vocabulary — ngram_size >= 4 and text
+ * that keeps non-ASCII code points (normalize_to_ascii=False).  Same reference functions as above.
+ * The host supplies an order-preserving dense alphabet: `bits` = ceil(log2(#symbols)), ngram*bits <= 64.
+ *   sym_width 1: `symbols` are bytes, lut[256] maps a byte to its symbol id after case folding / stripping
+ *                (0xff = deleted by the default regex);
+ *   sym_width 4: `symbols` are uint32 symbol ids (the host ran lower() / regex on the code points), lut unused.
+ * `offsets` count symbols.  Phase 1 writes, per document, its sorted distinct keys and term counts at the document's
+ * offset in scratch_key / scratch_tf and row_nnz[doc]; scratch_clean / scratch_sort serve documents longer than 256
+ * symbols.  Phase 2: indptr; ONE radix sort of all (document, key) runs -> vocabulary (vocab_keys[c] = key of column c,
+ * df[c]), column ids by a scan; values as sg_tfidf_finalize.  No device-to-host read-back inside either call.
+ * ------------------------------------------------------------------------- */
+int sg_tfidf64_count(const void *symbols /*[dev]*/, int sym_width, const int64_t *offsets /*[dev] n_docs+1*/,
+                     int64_t n_docs, int ngram, int bits, const uint8_t *lut /*[dev] 256 or NULL*/,
+                     uint32_t *scratch_clean /*[dev] total*/, uint64_t *scratch_sort /*[dev] total*/,
+                     uint64_t *scratch_key /*[dev] total*/, uint32_t *scratch_tf /*[dev] total*/,
+                     int32_t *row_nnz /*[dev] n_docs+1*/, void *stream);
+size_t sg_tfidf64_finalize_workspace_bytes(int64_t n_docs, int64_t total_symbols);
+int sg_tfidf64_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs, int64_t n_docs_fit, int64_t total_symbols,
+                        int ngram, int bits, int dtype, const uint64_t *scratch_key, const uint32_t *scratch_tf,
+                        int32_t *row_nnz, int64_t *indptr /*[dev] n_docs+1*/, int32_t *indices /*[dev] total*/,
+                        double *val64 /*[dev] total or NULL*/, float *val32 /*[dev] total*/,
+                        uint64_t *vocab_keys /*[dev] total*/, int32_t *df /*[dev] total*/,
+                        int32_t *vocab_size /*[dev] 1*/, int64_t *nnz_total /*[dev] 1*/, void *ws /*[dev]*/,
+                        size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * K2 — blocked CSR x CSR^T, thresholded, top-n per left row.
  * Replaces: StringGrouper._build_matches (sg.py:709-752), i.e. the
  * sp_matmul_topn block products (:737-743), the zip over right blocks (:746)

@@ -69,6 +69,13 @@ def customers():
     return df, df2
 
 
+UNICODE_TM = ["Acme\u2122 Corp", "ACME TM CORP", "AcmeTM Corp", "\u2116 5 Ltd", "No 5 Ltd", "no 5 ltd",
+              "Degree \u2103 Inc", "degree c inc", "plain ascii name"]
+UNICODE_RAW = ["Caf\u00e9 M\u00fcller GmbH", "Cafe Muller GmbH", "CAF\u00c9 M\u00dcLLER GMBH", "\u6771\u4eac\u682a\u5f0f\u4f1a\u793e",
+               "\u6771\u4eac\u682a\u5f0f\u4f1a\u793e\u30db\u30fc\u30eb\u30c7\u30a3\u30f3\u30b0\u30b9", "\u0130stanbul A.\u015e.", "istanbul a.s.",
+               "Stra\u00dfe 7 & S\u00f8n", "strasse 7 & son", "\U0001F600 emoji co", "emoji co"]
+
+
 def cases():
     """name -> (callable description for the test, result).  Every entry is replayed by
     tests/test_golden_api.py through string_grouper_b200 with the same arguments."""
@@ -121,6 +128,19 @@ def cases():
         ("cust_regex", ["names", "names2", None, None], {"min_similarity": 0.5, "regex": r"[aeiou]"}),
         ("cust_zero", ["names", ["whatever"], None, None], {"min_similarity": 0.0}),
         ("cust_blocks", ["names", "names2", None, None], {"min_similarity": 0.1, "n_blocks": (2, 3)}),
+        # keys beyond 32 bits (sort-based vocabulary of the device vectoriser)
+        ("cust_ngram5", ["names", "names2", None, None], {"min_similarity": 0.3, "ngram_size": 5}),
+        ("cust_ngram9", ["names", "names2", None, None], {"min_similarity": 0.1, "ngram_size": 9}),
+        ("cust_ngram12", ["names", "names2", None, None], {"min_similarity": 0.05, "ngram_size": 12}),
+        # str.lower() runs BEFORE NFKD, which can put capital ASCII back: 'TM', 'No', 'C' stay capital
+        ("sym_tm", [UNICODE_TM, None, None, None], {"min_similarity": 0.2}),
+        ("sym_tm_two", [UNICODE_TM, ["ACME TM CORP", "acmeTM corp", "no 5 ltd"], None, None], {"min_similarity": 0.2}),
+        # normalize_to_ascii=False keeps the non-ASCII code points (code-point n-grams)
+        ("raw_unicode", [UNICODE_RAW, None, None, None], {"min_similarity": 0.2, "normalize_to_ascii": False}),
+        ("raw_unicode_case", [UNICODE_RAW, UNICODE_RAW[:4], None, None],
+         {"min_similarity": 0.2, "normalize_to_ascii": False, "ignore_case": False}),
+        ("raw_unicode_ngram2", [UNICODE_RAW, None, None, None],
+         {"min_similarity": 0.2, "normalize_to_ascii": False, "ngram_size": 2}),
     ]:
         a = [S[x] if isinstance(x, str) else (pd.Series(x) if isinstance(x, list) else None) for x in args]
         kw2 = dict(kw)

@@ -798,8 +798,102 @@ def upload_strings(data, offsets, device=None):
     return d_bytes, d_off, total
 
 
+class DeviceVocabulary64:
+    """Sorted vocabulary of the general vectoriser (csrc/sg_tfidf64.cu): 64-bit keys over a dense alphabet."""
+
+    def __init__(self, keys, df, alphabet, bits, ngram, n_docs, vocab_size):
+        self.d_keys, self.d_df, self.alphabet = keys, df, alphabet
+        self.bits, self.ngram, self.n_docs, self.size = int(bits), int(ngram), int(n_docs), int(vocab_size)
+
+    def feature_names(self):
+        from ._ingest import decode_vocab_keys64
+        keys = self.d_keys[:self.size].cpu().numpy().view(np.uint64)
+        return decode_vocab_keys64(keys, self.ngram, self.bits, self.alphabet)
+
+
+DENSE_KEY_BITS = 21      # the dense key table (2^(7n) slots) is used up to trigrams; beyond: sorted vocabulary
+
+
+def tfidf_sorted(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None):
+    """K1, general form: 64-bit keys + sort-based vocabulary (ngram_size >= 4, or uint32 code points)."""
+    from . import _ingest
+    t = require_cuda()
+    L = _lib.load()
+    device = device or t.device("cuda", t.cuda.current_device())
+    n_docs = len(offsets) - 1
+    total = int(offsets[-1])
+    raw_bytes = None
+    if data.dtype == np.uint8:
+        lut, alphabet = _ingest.byte_alphabet(data, flags)
+        sym_width = 1
+        d_sym = t.from_numpy(np.ascontiguousarray(data)).to(device) if total else _empty(1, t.uint8, device)
+        d_lut = t.from_numpy(lut).to(device)
+        raw_bytes = d_sym
+    else:
+        alphabet = np.unique(data)
+        ids = np.searchsorted(alphabet, data).astype(np.uint32)
+        sym_width = 4
+        d_sym = t.from_numpy(ids.view(np.int32)).to(device) if total else _empty(1, t.int32, device)
+        d_lut = None
+    bits = _ingest.symbol_bits(len(alphabet))
+    if int(ngram) * bits > 64:
+        raise NotImplementedError(
+            "ngram_size=%d over an alphabet of %d distinct characters needs %d-bit n-gram keys; the device vectoriser "
+            "packs keys into 64 bits (ngram_size * ceil(log2(alphabet)) <= 64)" % (ngram, len(alphabet), ngram * bits))
+    d_off = t.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(device)
+    TRANSFER_BYTES["h2d"] += int(total * sym_width + 8 * len(offsets))
+    np_dtype = np.float32 if np.dtype(dtype) == np.float32 else np.float64
+    s_clean = _empty(total, t.int32, device)
+    s_sort = _empty(total, t.int64, device)
+    s_key = _empty(total, t.int64, device)
+    s_tf = _empty(total, t.int32, device)
+    row_nnz = _empty(n_docs + 1, t.int32, device)
+    _lib.check(L.sg_tfidf64_count(_ptr(d_sym), sym_width, _ptr(d_off), n_docs, int(ngram), bits, _ptr(d_lut),
+                                  _ptr(s_clean), _ptr(s_sort), _ptr(s_key), _ptr(s_tf), _ptr(row_nnz), _stream()))
+    indptr = _empty(n_docs + 1, t.int64, device)
+    indices = _empty(total, t.int32, device)
+    val32 = _empty(total, t.float32, device)
+    val64 = _empty(total, t.float64, device) if np_dtype == np.float64 else None
+    vocab_keys = _empty(total, t.int64, device)
+    df = _empty(total, t.int32, device)
+    tail = t.zeros(2, dtype=t.int64, device=device)         # [0] V (int32 view), [1] nnz
+    ws_bytes = int(L.sg_tfidf64_finalize_workspace_bytes(n_docs, total))
+    ws = _empty(ws_bytes, t.uint8, device)
+    dt = _lib.SG_DTYPE_F32 if np_dtype == np.float32 else _lib.SG_DTYPE_F64
+    _lib.check(L.sg_tfidf64_finalize(_ptr(d_off), n_docs, n_docs, total, int(ngram), bits, dt, _ptr(s_key), _ptr(s_tf),
+                                     _ptr(row_nnz), _ptr(indptr), _ptr(indices), _ptr(val64), _ptr(val32),
+                                     _ptr(vocab_keys), _ptr(df), ctypes.c_void_p(tail.data_ptr()),
+                                     ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["tfidf"] += 7
+    n_master = int(n_master)
+    head = t.cat([tail, indptr[n_master:n_master + 1]]).cpu().numpy()
+    V = int(head[0:1].view(np.int32)[0])
+    nnz = int(head[1])
+    split = int(head[2])
+    val = val64 if np_dtype == np.float64 else val32
+    vocab = DeviceVocabulary64(vocab_keys, df, alphabet, bits, ngram, n_docs, V)
+    if stats is not None:
+        stats.update(n_docs=n_docs, total_bytes=total, nnz=nnz, vocab=V, h2d_bytes=int(total * sym_width + 8 * len(offsets)),
+                     vectoriser="sorted vocabulary, %d-bit keys" % (int(ngram) * bits))
+        if raw_bytes is not None:
+            stats["raw"] = RawStrings(raw_bytes, d_off, n_master, n_docs)
+    master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
+    master.nnz_parent = nnz
+    if n_master == n_docs:
+        return master, None, vocab
+    dup = DeviceCSR((n_docs - n_master, V), indptr[n_master:], indices, val, val32, nnz - split, np_dtype, 1.0,
+                    base=split)
+    dup.nnz_parent = nnz
+    return master, dup, vocab
+
+
 def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None, df_allreduce=None, n_docs_fit=None):
-    """K1 from host buffers: packed ASCII strings (master ++ duplicates) -> TF-IDF CSR in HBM."""
+    """K1 from host buffers: packed strings (master ++ duplicates) -> TF-IDF CSR in HBM.  uint8 `data` = ASCII bytes
+    (dense key table up to trigrams), anything else goes through the sorted-vocabulary vectoriser."""
+    if data.dtype != np.uint8 or 7 * int(ngram) > DENSE_KEY_BITS:
+        if df_allreduce is not None:
+            raise NotImplementedError("the sharded vectoriser (df all-reduce) needs ASCII text and ngram_size <= 3")
+        return tfidf_sorted(data, offsets, n_master, ngram, flags, dtype, device=device, stats=stats)
     d_bytes, d_off, total = upload_strings(data, offsets, device)
     TRANSFER_BYTES["h2d"] += int(total + 8 * len(offsets))
     if stats is not None:

@@ -279,7 +279,8 @@ class StringGrouper(object):
         approx_bytes = (sum(int(s.str.len().sum()) for s in series)
                         if shard and world_size > 1 and len(series) == 2 else 0)
         stats = {}
-        if shard and world_size > 1 and len(series) == 2 and _dist.shard_vectorise(approx_bytes):
+        if (shard and world_size > 1 and len(series) == 2 and cfg.ngram_size <= 3 and cfg.normalize_to_ascii
+                and _dist.shard_vectorise(approx_bytes)):
             # two Series over several GPUs: every rank vectorises only its blocks of master and duplicates rows;
             # document frequencies are all-reduced (NCCL), the duplicate matrix is all-gathered over NVLink,
             # the master block stays local and is this rank's share of the left rows of _build_matches.

@@ -61,8 +61,12 @@ def _device_analyzer(s, ngram, flags):
 
 
 def tfidf(data, offsets, n_master, ngram, flags, dtype, device=None, stats=None):
-    raw = bytes(np.asarray(data, dtype=np.uint8))
-    docs = [raw[offsets[i]:offsets[i + 1]].decode("ascii") for i in range(len(offsets) - 1)]
+    if np.asarray(data).dtype == np.uint32:         # code points of text that keeps non-ASCII characters (flags == 0)
+        docs = [np.asarray(data[offsets[i]:offsets[i + 1]], dtype=np.uint32).tobytes().decode("utf-32-le", "surrogatepass")
+                for i in range(len(offsets) - 1)]
+    else:
+        raw = bytes(np.asarray(data, dtype=np.uint8))
+        docs = [raw[offsets[i]:offsets[i + 1]].decode("ascii") for i in range(len(offsets) - 1)]
     vec = TfidfVectorizer(min_df=1, analyzer=lambda s: _device_analyzer(s, ngram, flags), dtype=dtype)
     if docs and any(len(_device_analyzer(d, ngram, flags)) for d in docs):
         vec.fit(docs)

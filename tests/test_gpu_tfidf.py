@@ -43,7 +43,10 @@ def test_matrix_equals_reference_golden():
 
 
 @pytest.mark.parametrize("kw", [{}, {"ngram_size": 2}, {"ngram_size": 4}, {"ngram_size": 1}, {"ignore_case": False},
-                                {"tfidf_matrix_dtype": np.float32}, {"regex": r"[aeiou\s]"}])
+                                {"tfidf_matrix_dtype": np.float32}, {"regex": r"[aeiou\s]"},
+                                # sorted-vocabulary vectoriser (csrc/sg_tfidf64.cu): keys beyond 21 bits
+                                {"ngram_size": 5}, {"ngram_size": 7, "tfidf_matrix_dtype": np.float32},
+                                {"ngram_size": 9, "ignore_case": False}, {"ngram_size": 4, "regex": r"[aeiou\s]"}])
 def test_matrix_equals_sklearn_oracle(kw):
     from oracle import pipeline as P
     master = make_names(6000, seed=31) + EDGE + ["Q" * 1000, "lorem ipsum " * 60]
@@ -55,6 +58,57 @@ def test_matrix_equals_sklearn_oracle(kw):
     rtol = 1e-14 if dtype == np.float64 else 2e-6
     _assert_same_csr(m, rm, rtol)
     _assert_same_csr(d, rd, rtol)
+
+
+UNICODE = ["Caf\u00e9 M\u00fcller GmbH", "Cafe Muller GmbH", "CAF\u00c9 M\u00dcLLER GMBH", "\u6771\u4eac\u682a\u5f0f\u4f1a\u793e",
+           "\u6771\u4eac\u682a\u5f0f\u4f1a\u793e\u30db\u30fc\u30eb\u30c7\u30a3\u30f3\u30b0\u30b9", "\u0130stanbul A.\u015e.", "istanbul a.s.",
+           "Stra\u00dfe 7 & S\u00f8n", "strasse\u00a07\u2003& son", "\U0001F600 emoji co", "emoji co", "", "\u00e9"]
+
+
+@pytest.mark.parametrize("kw", [{}, {"ngram_size": 2}, {"ignore_case": False}, {"tfidf_matrix_dtype": np.float32},
+                                {"ngram_size": 4}])
+def test_code_point_ngrams_equal_sklearn_oracle(kw):
+    """normalize_to_ascii=False keeps the non-ASCII characters: n-grams over code points (string_grouper.py:374-378),
+    Python's lower() and the regex's Unicode white space handled like the reference."""
+    from oracle import pipeline as P
+    master = make_names(800, seed=33) + UNICODE
+    dupes = UNICODE[:5] + make_names(100, seed=34)
+    sg, m, d = _device_matrices(master, dupes, normalize_to_ascii=False, **kw)
+    okw = dict(kw)
+    dtype = okw.pop("tfidf_matrix_dtype", np.float64)
+    rm, rd, vec = P.tf_idf_matrices(master, dupes, dtype=dtype, normalize_to_ascii=False, **okw)
+    rtol = 1e-14 if dtype == np.float64 else 2e-6
+    _assert_same_csr(m, rm, rtol)
+    _assert_same_csr(d, rd, rtol)
+    vocab = vec.vocabulary_
+    assert sg._vocabulary.feature_names() == sorted(vocab, key=vocab.get)
+
+
+def test_sorted_vocabulary_feature_names_and_key_limit():
+    from oracle import pipeline as P
+    from string_grouper_b200 import StringGrouper
+    names = make_names(3000, seed=35)
+    sg = StringGrouper(pd.Series(names), ngram_size=6)
+    sg._get_tf_idf_matrices()
+    _, _, vec = P.tf_idf_matrices(names, ngram_size=6)
+    vocab = vec.vocabulary_
+    assert sg._vocabulary.feature_names() == sorted(vocab, key=vocab.get)
+    assert "64-bit" in sg._last_stats.get("vectoriser", "") or "bit keys" in sg._last_stats.get("vectoriser", "")
+    # n * ceil(log2(alphabet)) > 64: a clear error instead of a wrong answer
+    with pytest.raises(NotImplementedError):
+        StringGrouper(pd.Series(names), ngram_size=14)._get_tf_idf_matrices()
+
+
+def test_capital_ascii_from_nfkd_is_not_folded_again():
+    """str.lower() runs before NFKD in the reference analyzer (:372-375); NFKD of the trade-mark / numero / degree
+    signs yields CAPITAL ASCII that must survive ('acmeTMcorp', not 'acmetmcorp')."""
+    from oracle import pipeline as P
+    texts = ["Acme\u2122 Corp", "ACME TM CORP", "AcmeTM Corp", "\u2116 5 Ltd", "No 5 Ltd", "Degree \u2103 Inc",
+             "plain ascii"] + make_names(200, seed=36)
+    sg, m, _ = _device_matrices(texts)
+    rm, _, vec = P.tf_idf_matrices(texts)
+    _assert_same_csr(m, rm, 1e-14)
+    assert "eTM" in sg._vocabulary.feature_names()
 
 
 def test_reference_fixture_build_matrix():
