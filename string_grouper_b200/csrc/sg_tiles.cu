@@ -38,11 +38,9 @@ struct __align__(16) TileDesc {
     int n_dist;             // distinct features of the tile = buckets
 };
 
-constexpr int TL_LONG = 64;          // buckets from this length on are streamed by the whole warp
 constexpr int TL_W = 256;            // columns per tile (accumulator: 256 x u32 = 1 KB per warp)
 constexpr int TL_CBUF = 96;          // candidate buffer entries per warp
 constexpr float TL_FIX = 32768.f;    // weights in 2^-15 units, products in 2^-30 units
-constexpr int TL_WARP_BYTES = TL_W * 4 + 64 * 4 + 32 * 8 + TL_CBUF * 8;
 constexpr int TL_HEAD_BYTES = 128;   // mbarrier, item broadcast, survivor count
 
 __host__ __device__ __forceinline__ int a16(int x) { return (x + 15) & ~15; }
@@ -299,11 +297,19 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
                 } else if (nf > 0) {
                     __half2 ub2 = __float2half2_rn(0.f);
                     const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
-                    for (int k = 0; k < nk; ++k) {
-                        const int fk = __shfl_sync(FULL, f0, k);
-                        const __half2 ak2 = __shfl_sync(FULL, a2, k);
-                        const uint32_t m = mrow[(int64_t)fk * half_tp];
-                        ub2 = __hfma2(ak2, *reinterpret_cast<const __half2 *>(&m), ub2);
+                    // eight block-maxima loads in flight per lane (the table is L2-resident, the loop is latency-bound)
+                    for (int k0 = 0; k0 < nk; k0 += 8) {
+                        uint32_t m[8];
+                        __half2 ak[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int kk = k0 + j;
+                            const int fk = __shfl_sync(FULL, f0, kk & 31);
+                            ak[j] = __shfl_sync(FULL, a2, kk & 31);
+                            m[j] = kk < nk ? mrow[(int64_t)fk * half_tp] : 0u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ub2 = __hfma2(ak[j], *reinterpret_cast<const __half2 *>(&m[j]), ub2);
                     }
                     const float2 ub = __half22float2(ub2);
                     const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
@@ -328,151 +334,54 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
 // ---------------------------------------------------------------------------
 // candidates
 // ---------------------------------------------------------------------------
-constexpr int tl_min_ctas(int nw) { return nw == 16 ? 1 : 3; }
-
-struct WarpCtx {
-    uint32_t *acc;          // TL_W partial scores, 2^-30 units
-    uint32_t *flags;        // bucket-start bits of the concatenated list
-    int2 *dk;               // per non-empty short bucket: {posting index - start in the list, left weight}
-    int2 *cbuf;             // buffered candidates {left rank, column position}
-    int ccount;
-};
-
-__device__ __forceinline__ void flush_candidates(WarpCtx &cx, int lane, const int32_t *__restrict__ perm_a,
-                                                 int64_t row_begin, const int32_t *__restrict__ perm_b,
-                                                 int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
-                                                 unsigned long long cap, unsigned long long *cand_count) {
-    __syncwarp();
-    if (cx.ccount > 0) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)cx.ccount);
-        base = __shfl_sync(FULL, base, 0);
-        for (int i = lane; i < cx.ccount; i += 32) {
-            const int2 c = cx.cbuf[i];
-            if (base + i < cap) {
-                cand_row[base + i] = (int32_t)(perm_a ? perm_a[c.x] : row_begin + c.x);
-                cand_col[base + i] = perm_b ? perm_b[c.y] : c.y;
-            }
-        }
-        cx.ccount = 0;
-    }
-    __syncwarp();
+// shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loop)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128z(uint32_t a) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// old = (pred ? atomicAdd(shared a, v) : 0), without a branch
+__device__ __forceinline__ uint32_t atoms_add_if(uint32_t a, uint32_t v, bool pred) {
+    uint32_t old;
+    asm volatile(
+        "{ .reg .pred p; setp.ne.u32 p, %3, 0; mov.u32 %0, 0; @p atom.shared.add.u32 %0, [%1], %2; }"
+        : "=r"(old)
+        : "r"(a), "r"(v), "r"((unsigned)pred)
+        : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t lds32_if(uint32_t a, bool pred) {
+    uint32_t v;
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; mov.u32 %0, 0; @p ld.shared.u32 %0, [%1]; }"
+                 : "=r"(v)
+                 : "r"(a), "r"((unsigned)pred));
+    return v;
 }
 
-// report the columns whose partial score crossed the threshold in this step
-#define TL_EMIT(crossed_, colbyte_)                                                                       \
-    do {                                                                                                  \
-        const unsigned em_ = __ballot_sync(FULL, (crossed_));                                             \
-        if (em_) {                                                                                        \
-            if ((crossed_)) cx.cbuf[cx.ccount + __popc(em_ & lt_mask)] = make_int2(rank_id, col0 + ((int)(colbyte_) >> 2)); \
-            cx.ccount += __popc(em_);                                                                     \
-            if (cx.ccount > TL_CBUF - 32)                                                                 \
-                flush_candidates(cx, lane, perm_a, row_begin, perm_b, cand_row, cand_col, cap, cand_count);   \
-        }                                                                                                 \
-    } while (0)
-
-// One (left row, tile) pair: buckets of the row's kept features through the bitmap directory, long buckets streamed
-// by the warp, all others walked as one concatenated list; columns whose partial score crosses the threshold are
-// buffered as candidates.
-#define TL_PAIR(rank_id_, info_, fa_first_)                                                                         \
-    do {                                                                                                            \
-        const int rank_id = (rank_id_);                                                                             \
-        const int cur_p0 = (info_).x, cur_nf = (info_).y;                                                           \
-        const float thr_r = __int_as_float((info_).z);                                                              \
-        const float xp = __int_as_float((info_).w);                                                                 \
-        const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;                                \
-        const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));                   \
-        bool touched = false;                                                                                       \
-        ++n_pairs;                                                                                                  \
-        for (int fb = 0; fb < cur_nf; fb += 32) {                                                                   \
-            int2 e_fa = (fa_first_);                                                                                \
-            if (fb > 0) {                                                                                           \
-                e_fa = make_int2(0, 0);                                                                             \
-                if (fb + lane < cur_nf) e_fa = lpack[(int64_t)cur_p0 + fb + lane];                                  \
-            }                                                                                                       \
-            int len = 0, o0 = 0;                                                                                    \
-            if (fb + lane < cur_nf) {                                                                               \
-                const unsigned f = (unsigned)e_fa.x;                                                                \
-                const uint32_t bmw = bitmap[f >> 5];                                                                \
-                if ((bmw >> (f & 31)) & 1u) {                                                                       \
-                    const int jb = (int)prefix[f >> 5] + __popc(bmw & ((1u << (f & 31)) - 1u));                     \
-                    o0 = off[jb];                                                                                   \
-                    len = (int)off[jb + 1] - o0;                                                                    \
-                }                                                                                                   \
-            }                                                                                                       \
-            const unsigned aq = (unsigned)e_fa.y;                                                                   \
-            unsigned lm = __ballot_sync(FULL, len >= TL_LONG);                                                      \
-            while (lm) {                                                                                            \
-                const int s_ = __ffs(lm) - 1;                                                                       \
-                lm &= lm - 1;                                                                                       \
-                const int b0 = __shfl_sync(FULL, o0, s_);                                                           \
-                const int b1 = b0 + __shfl_sync(FULL, len, s_);                                                     \
-                const unsigned ak = __shfl_sync(FULL, aq, s_);                                                      \
-                n_walked += (unsigned)(b1 - b0);                                                                    \
-                for (int p = b0; p < b1; p += 32) {                                                                 \
-                    bool crossed = false;                                                                           \
-                    unsigned cb = 0;                                                                                \
-                    if (p + lane < b1) {                                                                            \
-                        const uint32_t e = post[p + lane];                                                          \
-                        const unsigned x = (e >> 16) * ak;                                                          \
-                        cb = e & 0xffffu;                                                                           \
-                        const unsigned old = atomicAdd(                                                             \
-                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
-                        crossed = old <= thr_c && old + x > thr_c;                                                  \
-                    }                                                                                               \
-                    TL_EMIT(crossed, cb);                                                                           \
-                }                                                                                                   \
-                touched = true;                                                                                     \
-            }                                                                                                       \
-            const int ln = len >= TL_LONG ? 0 : len;                                                                \
-            int incl = ln;                                                                                          \
-            _Pragma("unroll") for (int o = 1; o < 32; o <<= 1) {                                                    \
-                const int up = __shfl_up_sync(FULL, incl, o);                                                       \
-                if (lane >= o) incl += up;                                                                          \
-            }                                                                                                       \
-            const int total = __shfl_sync(FULL, incl, 31);                                                          \
-            if (total > 0) {                                                                                        \
-                touched = true;                                                                                     \
-                n_walked += (unsigned)total;                                                                        \
-                const unsigned nz = __ballot_sync(FULL, ln > 0);                                                    \
-                if (ln > 0) {                                                                                       \
-                    const int st = incl - ln;                                                                       \
-                    cx.dk[__popc(nz & lt_mask)] = make_int2(o0 - st, (int)aq);                                      \
-                    atomicOr(&cx.flags[st >> 5], 1u << (st & 31));                                                  \
-                }                                                                                                   \
-                __syncwarp();                                                                                       \
-                int kbase = -1;                                                                                     \
-                for (int s0 = 0; s0 < total; s0 += 32) {                                                            \
-                    const uint32_t fw = cx.flags[s0 >> 5];                                                          \
-                    const int k = kbase + __popc(fw & le_mask);                                                     \
-                    kbase += __popc(fw);                                                                            \
-                    __syncwarp();                                                                                   \
-                    if (lane == 0) cx.flags[s0 >> 5] = 0u;                                                          \
-                    bool crossed = false;                                                                           \
-                    unsigned cb = 0;                                                                                \
-                    if (s0 + lane < total) {                                                                        \
-                        const int2 dd = cx.dk[k];                                                                   \
-                        const uint32_t e = post[dd.x + s0 + lane];                                                  \
-                        const unsigned x = (e >> 16) * (unsigned)dd.y;                                              \
-                        cb = e & 0xffffu;                                                                           \
-                        const unsigned old = atomicAdd(                                                             \
-                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
-                        crossed = old <= thr_c && old + x > thr_c;                                                  \
-                    }                                                                                               \
-                    TL_EMIT(crossed, cb);                                                                           \
-                }                                                                                                   \
-                __syncwarp();                                                                                       \
-            }                                                                                                       \
-        }                                                                                                           \
-        if (touched) {                                                                                              \
-            __syncwarp();                                                                                           \
-            _Pragma("unroll") for (int c = 0; c < TL_W * 4 / 16 / 32; ++c)                                          \
-                reinterpret_cast<uint4 *>(cx.acc)[c * 32 + lane] = zero4;                                           \
-            __syncwarp();                                                                                           \
-        }                                                                                                           \
-    } while (0)
-
-__host__ __device__ constexpr int tl_list(int nw) { return nw * 256; }     // survivor ranks per scan round (every warp scans 256 ranks)
+constexpr int TL_SW = 16;                           // lanes per (left row, tile) pair: a warp works on 32 / TL_SW pairs at once
+constexpr int TL_G = 32 / TL_SW;
+// per warp: one accumulator tile per pair group, 256 start-flag words, 32 bucket records, the candidate buffer
+constexpr int TL_WARP_BYTES2 = TL_G * TL_W * 4 + 256 * 4 + 32 * 8 + TL_CBUF * 8;
+constexpr int tl_min_ctas(int nw) { return nw == 16 ? 1 : 2; }
+__host__ __device__ constexpr int tl_list(int nw) { return nw * 256; }     // survivor ranks per scan round
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, tl_min_ctas(NW))
@@ -492,16 +401,17 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
     uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + TL_HEAD_BYTES);
     unsigned char *stage = smem + TL_HEAD_BYTES + tl_list(NW) * 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
-    unsigned char *wa = stage + stage_bytes + (size_t)warp * TL_WARP_BYTES;
-    WarpCtx cx;
-    cx.acc = reinterpret_cast<uint32_t *>(wa);
-    cx.flags = reinterpret_cast<uint32_t *>(wa + TL_W * 4);
-    cx.dk = reinterpret_cast<int2 *>(wa + TL_W * 4 + 64 * 4);
-    cx.cbuf = reinterpret_cast<int2 *>(wa + TL_W * 4 + 64 * 4 + 32 * 8);
-    cx.ccount = 0;
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    for (int c = lane; c < (TL_W * 4 + 64 * 4) / 16; c += 32) reinterpret_cast<uint4 *>(wa)[c] = zero4;
+    const int g = lane / TL_SW, gl = lane % TL_SW;              // pair group of the lane, lane inside the group
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t stage_s = smem_s + TL_HEAD_BYTES + tl_list(NW) * 4;
+    const uint32_t warp_s = stage_s + stage_bytes + warp * TL_WARP_BYTES2;
+    const uint32_t acc_s = warp_s + g * (TL_W * 4);                         // this group's accumulator tile
+    const uint32_t flags_s = warp_s + TL_G * TL_W * 4 + g * (1024 / TL_G);  // this group's start-flag words
+    const uint32_t dk_s = warp_s + TL_G * TL_W * 4 + 1024 + g * (TL_SW * 8);
+    const uint32_t cbuf_s = warp_s + TL_G * TL_W * 4 + 1024 + 256;
+    int ccount = 0;
+    for (int c = lane; c < (TL_G * TL_W * 4 + 1024) / 16; c += 32) sts128z(warp_s + c * 16);
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         *s_count = 0;
@@ -510,7 +420,27 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
 
     const unsigned long long n_items = (unsigned long long)T * (unsigned long long)n_seg;
     unsigned parity = 0;
-    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added by this warp
+    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added (per lane group)
+
+    // buffered candidates -> global list (one atomic per flush)
+    auto flush = [&]() {
+        __syncwarp();
+        if (ccount > 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)ccount);
+            base = __shfl_sync(FULL, base, 0);
+            for (int i = lane; i < ccount; i += 32) {
+                const uint2 c = lds64(cbuf_s + i * 8);
+                if (base + i < cap) {
+                    cand_row[base + i] = (int32_t)(perm_a ? perm_a[c.x] : row_begin + c.x);
+                    cand_col[base + i] = perm_b ? perm_b[c.y] : (int32_t)c.y;
+                }
+            }
+            ccount = 0;
+        }
+        __syncwarp();
+    };
+
     for (;;) {
         // ---- next (tile, rank segment); its blob goes into shared memory by bulk copies (TMA)
         if (threadIdx.x == 0) {
@@ -532,11 +462,10 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         const int t = (int)(it / (unsigned long long)n_seg);
         const int64_t seg = (int64_t)(it % (unsigned long long)n_seg);
         const TileDesc d = tdesc[t];
-        const uint32_t *post = reinterpret_cast<const uint32_t *>(stage);
-        const uint32_t *bitmap = reinterpret_cast<const uint32_t *>(stage + a16(4 * d.n_post));
-        const unsigned short *prefix = reinterpret_cast<const unsigned short *>(stage + a16(4 * d.n_post) + 4 * bw);
-        const unsigned short *off =
-            reinterpret_cast<const unsigned short *>(stage + a16(4 * d.n_post) + 4 * bw + a16(2 * bw));
+        const uint32_t post_s = stage_s;
+        const uint32_t bitmap_s = stage_s + a16(4 * d.n_post);
+        const uint32_t prefix_s = bitmap_s + 4 * bw;
+        const uint32_t off_s = prefix_s + a16(2 * bw);
         const float tbound = tile_bound[t];
         const int col0 = t * TL_W;
         const int64_t rank_lo = seg * seg_ranks;
@@ -573,47 +502,126 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
                     mbar_wait(mbar, parity);
                     staged = true;
                 }
-                // ---- this warp's pairs: list entries warp, warp + NW, ...; row record two ahead, features one ahead
-                int i = warp;
+                // ---- this warp's pairs: TL_G list entries at a time (one per lane group), dealt round-robin over the
+                // warps; the row record of the next entry and its first features are fetched one step ahead
+                int i = warp * TL_G + g;
                 int r_c = 0, r_n = 0;
                 int4 info_c = make_int4(0, 0, 0, 0), info_n = info_c;
-                int2 fa_c = make_int2(0, 0);
+                int2 fa_c = make_int2(0, 0), fb_c = fa_c;
                 if (i < count) {
                     r_c = (int)s_list[i];
                     info_c = rowinfo[r_c];
+                    if (gl < info_c.y) fa_c = lpack[(int64_t)info_c.x + gl];
+                    if (gl + TL_SW < info_c.y) fb_c = lpack[(int64_t)info_c.x + gl + TL_SW];
                 }
-                if (i + NW < count) {
-                    r_n = (int)s_list[i + NW];
+                if (i + NW * TL_G < count) {
+                    r_n = (int)s_list[i + NW * TL_G];
                     info_n = rowinfo[r_n];
                 }
-                if (i < count && lane < info_c.y) fa_c = lpack[(int64_t)info_c.x + lane];
-                while (i < count) {
-                    int2 fa_n = make_int2(0, 0);
-                    if (i + NW < count && lane < info_n.y) fa_n = lpack[(int64_t)info_n.x + lane];
+                for (int i0 = warp * TL_G; i0 < count; i0 += NW * TL_G) {
+                    int2 fa_n = make_int2(0, 0), fb_n = fa_n;
+                    if (gl < info_n.y) fa_n = lpack[(int64_t)info_n.x + gl];
+                    if (gl + TL_SW < info_n.y) fb_n = lpack[(int64_t)info_n.x + gl + TL_SW];
                     int r_nn = 0;
                     int4 info_nn = make_int4(0, 0, 0, 0);
-                    if (i + 2 * NW < count) {
-                        r_nn = (int)s_list[i + 2 * NW];
+                    if (i + 2 * NW * TL_G < count) {
+                        r_nn = (int)s_list[i + 2 * NW * TL_G];
                         info_nn = rowinfo[r_nn];
                     }
-                    TL_PAIR(r_c, info_c, fa_c);
-                    r_c = r_n; info_c = info_n; fa_c = fa_n;
+                    // ---- TL_G (left row, tile) pairs, one per lane group (nf == 0: no pair in this group)
+                    const int nf = info_c.y;
+                    const float thr_r = __int_as_float(info_c.z);
+                    const float xp = __int_as_float(info_c.w);
+                    const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;
+                    const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));
+                    if (gl == 0 && nf > 0) ++n_pairs;
+                    bool touched = false;
+                    for (int fb = 0; __any_sync(FULL, fb < nf); fb += TL_SW) {
+                        int2 e_fa = fb == 0 ? fa_c : fb_c;
+                        const bool active = fb + gl < nf;
+                        if (fb >= 2 * TL_SW) {           // rows with more than 2 * TL_SW kept features: fetched on demand
+                            e_fa = make_int2(0, 0);
+                            if (active) e_fa = lpack[(int64_t)info_c.x + fb + gl];
+                        }
+                        // bucket of the lane's feature through the bitmap directory (all loads unconditional: feature
+                        // 0 for idle lanes)
+                        const unsigned f = active ? (unsigned)e_fa.x : 0u;
+                        const uint32_t bmw = lds32(bitmap_s + ((f >> 5) << 2));
+                        const uint32_t pre = lds16(prefix_s + ((f >> 5) << 1));
+                        const uint32_t jb = pre + __popc(bmw & ((1u << (f & 31)) - 1u));
+                        const uint32_t o0 = lds16(off_s + (jb << 1));
+                        const uint32_t o1 = lds16(off_s + (jb << 1) + 2);
+                        const int len = (active && ((bmw >> (f & 31)) & 1u)) ? (int)(o1 - o0) : 0;
+                        // the group's buckets as ONE concatenated list; the owner of a position is the number of bucket
+                        // starts at or before it (start bits + popc)
+                        int incl = len;
+#pragma unroll
+                        for (int o = 1; o < TL_SW; o <<= 1) {
+                            const int up = __shfl_up_sync(FULL, incl, o, TL_SW);
+                            if (gl >= o) incl += up;
+                        }
+                        const int total = __shfl_sync(FULL, incl, TL_SW - 1, TL_SW);
+                        int max_total = total;
+#pragma unroll
+                        for (int o = TL_SW; o < 32; o <<= 1) max_total = max(max_total, __shfl_xor_sync(FULL, max_total, o));
+                        if (max_total == 0) continue;
+                        touched = touched || total > 0;
+                        if (gl == 0) n_walked += (unsigned)total;
+                        const unsigned nz = __ballot_sync(FULL, len > 0);
+                        if (len > 0) {
+                            const int st = incl - len;
+                            const unsigned before = nz & lt_mask & (TL_SW == 32 ? FULL : (((1u << TL_SW) - 1u) << (g * TL_SW)));
+                            sts64(dk_s + __popc(before) * 8, (uint32_t)((int)o0 - st), (uint32_t)e_fa.y);
+                            reds_or(flags_s + ((st >> 5) << 2), 1u << (st & 31));
+                        }
+                        __syncwarp();
+                        int kb = -1, kb_next = -1;
+                        for (int s0 = 0; s0 < max_total; s0 += TL_SW) {
+                            const int item = s0 + gl;
+                            const uint32_t word = lds32(flags_s + ((item >> 5) << 2));
+                            if ((s0 & 31) == 0) {          // uniform: the step enters a new flag word
+                                kb = kb_next;
+                                kb_next = kb + __popc(word);
+                            }
+                            const bool in = item < total;
+                            const int k = in ? kb + __popc(word & ((2u << (item & 31)) - 1u)) : 0;
+                            const uint2 dd = lds64(dk_s + k * 8);
+                            const uint32_t e = lds32_if(post_s + (((int)dd.x + item) << 2), in);
+                            const uint32_t x = (e >> 16) * dd.y;
+                            const uint32_t cb = e & 0xffffu;
+                            const uint32_t old = atoms_add_if(acc_s + cb, x, in);
+                            const bool crossed = in && old <= thr_c && old + x > thr_c;
+                            const unsigned em = __ballot_sync(FULL, crossed);
+                            if (em) {
+                                if (crossed) sts64(cbuf_s + (ccount + __popc(em & lt_mask)) * 8, (uint32_t)r_c, (uint32_t)(col0 + (int)(cb >> 2)));
+                                ccount += __popc(em);
+                                if (ccount > TL_CBUF - 32) flush();
+                            }
+                        }
+                        __syncwarp();
+                        for (int w = gl; (w << 5) < total; w += TL_SW) sts32(flags_s + (w << 2), 0u);
+                        __syncwarp();
+                    }
+                    if (touched) {
+#pragma unroll
+                        for (int c = 0; c < TL_W * 4 / 16 / TL_SW; ++c) sts128z(acc_s + (c * TL_SW + gl) * 16);
+                    }
+                    __syncwarp();
+                    r_c = r_n; info_c = info_n; fa_c = fa_n; fb_c = fb_n;
                     r_n = r_nn; info_n = info_nn;
-                    i += NW;
+                    i += NW * TL_G;
                 }
             }
             __syncthreads();
             if (threadIdx.x == 0) *s_count = 0;
-            // (the next round's appends come after the next __syncthreads-separated scan loads; the reset is ordered
-            // before them by the barrier below)
             __syncthreads();
         }
         if (!staged) mbar_wait(mbar, parity);     // nothing survived: still consume the phase before the stage is reused
         parity ^= 1u;
         __syncthreads();      // every warp is done with the staged tile before the next one is copied over it
     }
-    flush_candidates(cx, lane, perm_a, row_begin, perm_b, cand_row, cand_col, cap, cand_count);
-    if (walk_stats && lane == 0) {
+    flush();
+    if (walk_stats && gl == 0) {
         atomicAdd(walk_stats, n_pairs);
         atomicAdd(walk_stats + 1, n_walked);
     }
@@ -746,7 +754,7 @@ int sg_tiles_filter(int64_t n_ranks, const void *rowinfo, const void *lpack, con
 }
 
 size_t sg_tiles_smem_bytes(int stage_bytes, int warps_per_cta) {
-    return (size_t)TL_HEAD_BYTES + (size_t)tl_list(warps_per_cta) * 4 + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES;
+    return (size_t)TL_HEAD_BYTES + (size_t)tl_list(warps_per_cta) * 4 + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES2;
 }
 
 int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begin, const void *rowinfo,
