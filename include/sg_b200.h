@@ -294,7 +294,8 @@ int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
                const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
                double *score_out /*[dev] n_cand*/, double keep_threshold, int32_t *keep_row /*[dev] n_cand or NULL*/,
                int32_t *keep_col /*[dev] n_cand or NULL*/, unsigned long long *keep_count /*[dev] 1 or NULL*/,
-               void *stream);
+               int32_t *row_cnt /*[dev] per left row - row_begin, zeroed by the caller, or NULL: += kept per row*/,
+               int64_t row_begin, void *stream);
 
 /*
  * Per-row selection: keep score > threshold (strict, sg.py:729/:740), at most
@@ -311,6 +312,22 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
                    double threshold, int64_t *out_indptr, int32_t *out_row, int32_t *out_col,
                    double *out_score, int64_t *out_nnz /*[dev] 1*/, int32_t *out_max_row /*[dev] 1*/,
                    void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * The same selection without global sorts (csrc/sg_select.cu): the survivors (already strictly above the threshold,
+ * counted per row by sg_rescore's `row_cnt`) are bucketed by row; rows of up to 32 survivors are ranked by one warp
+ * with a shuffle bitonic network, rows of up to sg_topn_rows_cap() by one CTA in shared memory.  When
+ * sg_row_count_max() reports a larger row the caller uses sg_topn_select instead.  Same outputs and tie rule.
+ */
+int sg_topn_rows_cap(void);
+int sg_row_count_max(int64_t n_rows, const int32_t *row_cnt /*[dev]*/, int32_t *out_max /*[dev] 1, zeroed*/,
+                     void *stream);
+size_t sg_topn_select_rows_workspace_bytes(int64_t n_cand, int64_t n_rows);
+int sg_topn_select_rows(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const double *score,
+                        int64_t row_begin, int64_t n_rows, int top_n, const int32_t *row_cnt /*[dev] n_rows*/,
+                        int64_t *out_indptr, int32_t *out_row, int32_t *out_col, double *out_score,
+                        int64_t *out_nnz /*[dev] 1*/, int32_t *out_max_row /*[dev] 1*/, void *ws, size_t ws_bytes,
+                        void *stream);
 
 /*
  * K3 — per-row top-n merge of column-block results.  Replaces sparse_dot_topn.zip_sp_matmul_topn(top_n, C_mats)

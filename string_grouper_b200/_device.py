@@ -38,6 +38,7 @@ K2_KERNEL = os.environ.get("SG_B200_KERNEL", "tiles").lower()
 TILE_MARGIN = 2e-5               # fp32 arithmetic of thresholds / norms and the f64 -> f32 copy of the values
 TILE_MARGIN_PER_FEATURE = 3.1e-5  # a_q * w_q / 2^30 vs a * w: both weights rounded to nearest 2^-15 (<= 2^-15 + 2^-32)
 TILE_WARPS = int(os.environ.get("SG_B200_TILE_WARPS", "8"))
+SELECT_MODE = os.environ.get("SG_B200_SELECT", "rows").lower()      # "rows" (per-row ranking) | "sort" (global sorts)
 
 
 def torch():
@@ -567,6 +568,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     rows_per_chunk = -(-n_rows // n_chunks)
     kept = []
     n_cand_total = 0
+    max_row_cnt = 0
+    row_cnt = t.zeros(n_rows + 1, dtype=t.int32, device=dev)      # survivors per left row (sg_rescore)
     for lo in range(0, n_rows, rows_per_chunk):
         hi = min(lo + rows_per_chunk, n_rows)
         perm_chunk = perm_a if (lo == 0 and hi == n_rows) else perm_a[lo:hi]
@@ -604,9 +607,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         counters.zero_()
         _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
                                 _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
-                                float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _stream()))
+                                float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _ptr(row_cnt), row_begin,
+                                _stream()))
         LAUNCH_COUNTS["rescore"] += 1
-        n_keep = int(counters[0].item())
+        if lo + rows_per_chunk >= n_rows:      # last chunk: the largest row rides along with the read-back
+            _lib.check(L.sg_row_count_max(n_rows, _ptr(row_cnt), c_queue, _stream()))      # counters[1], zeroed above
+        head = counters[:2].cpu().numpy()
+        n_keep, max_row_cnt = int(head[0]), int(head[1])
         mark(stats, "rescore")
         if n_chunks > 1:      # release the chunk-sized buffers, keep the survivors
             keep_row, keep_col, score = keep_row[:n_keep].clone(), keep_col[:n_keep].clone(), score[:n_keep].clone()
@@ -634,13 +641,28 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     out_col = _empty(n_cand, t.int32, dev)
     out_score = _empty(n_cand, t.float64, dev)
     tail = t.zeros(2, dtype=t.int64, device=dev)            # [0] out_nnz, [1] max_row (int32 view)
-    ws_bytes = int(L.sg_topn_select_workspace_bytes(n_cand, n_rows))
-    ws = _empty(ws_bytes, t.uint8, dev)
-    _lib.check(L.sg_topn_select(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(score), row_begin, n_rows, top_n,
-                                float(threshold), _ptr(out_indptr), _ptr(out_row), _ptr(out_col), _ptr(out_score),
-                                ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
-                                ws_bytes, _stream()))
-    LAUNCH_COUNTS["select"] += 7
+    if max_row_cnt <= int(L.sg_topn_rows_cap()) and SELECT_MODE != "sort":
+        # survivors bucketed by row, every row ranked on its own (warp shuffle network / one CTA in shared memory)
+        ws_bytes = int(L.sg_topn_select_rows_workspace_bytes(n_cand, n_rows))
+        ws = _empty(ws_bytes, t.uint8, dev)
+        _lib.check(L.sg_topn_select_rows(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(score), row_begin, n_rows, top_n,
+                                         _ptr(row_cnt), _ptr(out_indptr), _ptr(out_row), _ptr(out_col),
+                                         _ptr(out_score), ctypes.c_void_p(tail.data_ptr()),
+                                         ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws), ws_bytes, _stream()))
+        LAUNCH_COUNTS["select"] += 5
+        if stats is not None:
+            stats["select"] = "rows"
+    else:
+        # a row with more survivors than one CTA ranks in shared memory: three global radix sorts
+        ws_bytes = int(L.sg_topn_select_workspace_bytes(n_cand, n_rows))
+        ws = _empty(ws_bytes, t.uint8, dev)
+        _lib.check(L.sg_topn_select(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(score), row_begin, n_rows, top_n,
+                                    float(threshold), _ptr(out_indptr), _ptr(out_row), _ptr(out_col), _ptr(out_score),
+                                    ctypes.c_void_p(tail.data_ptr()), ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws),
+                                    ws_bytes, _stream()))
+        LAUNCH_COUNTS["select"] += 7
+        if stats is not None:
+            stats["select"] = "sort"
     th = tail.cpu().numpy()
     mark(stats, "select")
     nnz = int(th[0])

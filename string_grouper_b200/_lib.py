@@ -70,7 +70,11 @@ SIGNATURES = {
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _sz, _p]),
-    "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _p, _p]),
+    "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _p, _p, _i64, _p]),
+    "sg_topn_rows_cap": (_i32, []),
+    "sg_row_count_max": (_i32, [_i64, _p, _p, _p]),
+    "sg_topn_select_rows_workspace_bytes": (_sz, [_i64, _i64]),
+    "sg_topn_select_rows": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_topn_select_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_topn_select": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_topn_merge_workspace_bytes": (_sz, [_i64, _i64]),

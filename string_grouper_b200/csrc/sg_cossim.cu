@@ -433,7 +433,8 @@ __global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const 
                                const T *__restrict__ a_val, const int64_t *__restrict__ b_indptr,
                                const int32_t *__restrict__ b_idx, const T *__restrict__ b_val,
                                double *__restrict__ out, double keep_thr, int32_t *__restrict__ keep_row,
-                               int32_t *__restrict__ keep_col, unsigned long long *__restrict__ keep_count) {
+                               int32_t *__restrict__ keep_col, unsigned long long *__restrict__ keep_count,
+                               int32_t *__restrict__ row_cnt, int64_t row_begin) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int32_t r = 0, c = 0;
     double sc = 0.0;
@@ -458,6 +459,8 @@ __global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const 
         keep_row[w] = r;
         keep_col[w] = c;
         out[w] = sc;
+        if (row_cnt) atomicAdd(row_cnt + (r - row_begin), 1);       // survivors per row: sizes the row buckets of
+                                                                    // sg_topn_select_rows
     }
 }
 
@@ -739,21 +742,23 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
 int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const int64_t *a_indptr,
                const int32_t *a_indices, const void *a_val, const int64_t *b_indptr, const int32_t *b_indices,
                const void *b_val, int dtype, double *score_out, double keep_threshold, int32_t *keep_row,
-               int32_t *keep_col, unsigned long long *keep_count, void *stream_) {
+               int32_t *keep_col, unsigned long long *keep_count, int32_t *row_cnt, int64_t row_begin,
+               void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_cand <= 0) return SG_OK;
     if (keep_count && (!keep_row || !keep_col)) return fail(SG_ERR_INVALID, "keep_count needs keep_row and keep_col");
+    if (row_cnt && !keep_count) return fail(SG_ERR_INVALID, "row_cnt needs keep_count");
     const unsigned grid = (unsigned)((n_cand + 255) / 256);
     if (dtype == SG_DTYPE_F64)
         rescore_kernel<double><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
                                                      (const double *)a_val, b_indptr, b_indices,
                                                      (const double *)b_val, score_out, keep_threshold, keep_row,
-                                                     keep_col, keep_count);
+                                                     keep_col, keep_count, row_cnt, row_begin);
     else if (dtype == SG_DTYPE_F32)
         rescore_kernel<float><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
                                                     (const float *)a_val, b_indptr, b_indices,
                                                     (const float *)b_val, score_out, keep_threshold, keep_row,
-                                                    keep_col, keep_count);
+                                                    keep_col, keep_count, row_cnt, row_begin);
     else
         return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
     SG_LAUNCH_CHECK();

@@ -150,6 +150,34 @@ def test_row_chunks_and_adaptive_pruning_level(monkeypatch):
         assert np.array_equal(x, y)
 
 
+def test_row_selection_paths_agree(monkeypatch):
+    """per-row ranking (warp network for <= 32 survivors, one CTA for <= sg_topn_rows_cap) vs the three global sorts:
+    identical triples, including clusters of identical names far beyond top_n and a row count beyond the CTA path."""
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    base = make_names(9000, seed=17)
+    for big in (700, 5000):        # 700: CTA path; 5000 > sg_topn_rows_cap(): the caller falls back to the sorts
+        names = base + ["ACME HOLDINGS LLC"] * big + ["ACME HOLDINGS LLC %d" % (i % 7) for i in range(300)]
+        m, _, _ = P.tf_idf_matrices(names)
+        A = D.DeviceCSR.from_scipy(m)
+        out = {}
+        for mode in ("rows", "sort"):
+            monkeypatch.setattr(D, "SELECT_MODE", mode)
+            st = {}
+            for top_n in (20, 1, 3000):
+                got = D.cossim_topn(A, A, top_n, 0.8, stats=st)
+                out[(mode, top_n)] = got.host_triples() + (got.max_row,)
+            assert st["select"] == ("sort" if (mode == "sort" or big > 4096) else "rows")
+        for top_n in (20, 1, 3000):
+            a, b = out[("rows", top_n)], out[("sort", top_n)]
+            assert a[3] == b[3]
+            for x, y in zip(a[:3], b[:3]):
+                assert np.array_equal(x, y), (big, top_n)
+        ref = P.build_matches(m, m, None, 20, 0.8, n_threads=4)
+        cut = row_cutoffs(ref.indptr, ref.data, 20, len(names))
+        compare_triples(csr_triples(ref), out[("rows", 20)][:3], len(names), 0.8, cutoff_row=cut, label="clusters")
+
+
 def test_long_rows():
     """strings of several hundred characters (more than 32 features per row: several lane batches)."""
     from string_grouper_b200 import _device as D

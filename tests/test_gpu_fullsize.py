@@ -34,44 +34,79 @@ def test_full_size_structure(fitted):
     assert len(ml) > 4_000_000
 
 
-def test_full_size_is_tile_and_order_invariant(fitted):
-    """sum of checksums over two different tilings (block invariance, reference tests :191-336)."""
+def _threads():
+    import bench_cpu
+    return min(bench_cpu.usable_cores(), 16)
+
+
+def test_full_size_kernels_and_pruning_levels_agree(fitted):
+    """663k: the TMA-staged tile kernel at the default pruning level, the row kernel, and the UNPRUNED fp32 traversal
+    return bit-identical triples (block invariance, reference tests :191-336; a pruning bug at scale cannot cancel)."""
     from string_grouper_b200 import _device as D
     names, sg = fitted
     A, _ = sg._get_tf_idf_matrices()
-    a = D.cossim_topn(A, A, 20, 0.8, tile_w=768, warps=32)
-    b = D.cossim_topn(A, A, 20, 0.8, tile_w=1536, warps=16)
-    ta, tb = a.host_triples(), b.host_triples()
-    assert a.nnz == b.nnz
-    for x, y in zip(ta, tb):
-        assert np.array_equal(x, y)
+    st = {}
+    a = D.cossim_topn(A, A, 20, 0.8, stats=st)
+    assert st["kernel"] == "tiles" and st["prune"] > 0
+    b = D.cossim_topn(A, A, 20, 0.8, kernel="row", prune=0.0, acc="f32")
+    c = D.cossim_topn(A, A, 20, 0.8, kernel="row", tile_w=1536, warps=16)
+    ta = a.host_triples()
+    assert a.nnz == b.nnz == c.nnz
+    for other in (b.host_triples(), c.host_triples()):
+        for x, y in zip(ta, other):
+            assert np.array_equal(x, y)
 
 
-def test_full_size_sampled_rows_equal_oracle(fitted):
-    from oracle.sdt import sp_matmul_topn
-    from parity import compare_triples, row_cutoffs
+def test_full_size_all_pairs_equal_cpu_port(fitted):
+    """BASELINE.json's headline configuration, EVERY pair: the whole 663k product on the CPU port with the reference's
+    own block split (string_grouper.py:387-394 -> n_blocks (1, 166)), then fix-diagonal / symmetrise, against the CUDA
+    match list (SURVEY.md §8c parity definition, all 4.36 M pairs)."""
+    import bench_cpu
+    from oracle import pipeline as P
     from string_grouper_b200 import _device as D
     names, sg = fitted
     A, _ = sg._get_tf_idf_matrices()
-    full = A.to_scipy()
-    rng = np.random.default_rng(7)
-    rows = np.sort(rng.choice(N, size=1500, replace=False))
-    ref = sp_matmul_topn(full[rows], full.T.tocsr(), top_n=20, threshold=0.8, sort=True, n_threads=16)
-    got = D.cossim_topn(A, A, 20, 0.8)
-    gr, gc, gs = got.host_triples()
-    sel = np.isin(gr, rows)
-    pos = np.searchsorted(rows, gr[sel])
-    cut = row_cutoffs(ref.indptr, ref.data, 20, len(rows))
-    rr = np.repeat(np.arange(len(rows)), np.diff(ref.indptr))
-    st = compare_triples((rr, ref.indices, ref.data), (pos, gc[sel], gs[sel]), N, 0.8, tol=1e-9, cutoff_row=cut,
-                         label="663k sample")
-    assert st["common"] >= 0.97 * st["pairs_ref"]
+    full = A.to_scipy()                 # equal to the sklearn matrix: tests/test_gpu_tfidf.py
+    C = P.build_matches(full, full, P.guess_blocks(N, N), 20, 0.8, _threads())
+    S = P.symmetrize_fast(C)            # vectorised twin of the LIL restatement (tests/test_oracle.py)
+    ml = P.matches_list(S)
+    job = {"rows": N, "c_indptr": C.indptr.astype(np.int64), "c_indices": C.indices, "c_data": C.data,
+           "row": ml.master_side.to_numpy(), "col": ml.dupe_side.to_numpy(), "score": ml.similarity.to_numpy()}
+    pre = D.cossim_topn(A, A, 20, 0.8).host_triples()
+    got = sg._matches_list
+    par = bench_cpu.compare(job, pre, (got.master_side.to_numpy(), got.dupe_side.to_numpy(), got.similarity.to_numpy()))
+    assert par["ok"], par
+    assert par["product"]["max_abs_err"] <= 1e-9 and par["match_list"]["max_abs_err"] <= 1e-9
+    assert par["match_list"]["pairs_ref"] > 4_000_000
+    assert par["product"]["common"] >= 0.97 * par["product"]["pairs_ref"]     # the rest: top-n ties in clusters of identical names
+    assert sg._true_max_n_matches == int(np.diff(C.indptr).max())
 
 
-def test_two_series_large_sampled_rows_equal_oracle():
-    """config-4-shaped run (master x duplicates, min_similarity 0.7) at 400k x 150k."""
-    from oracle.sdt import sp_matmul_topn
-    from parity import compare_triples, row_cutoffs
+def test_config2_100k_all_pairs_equal_cpu_port():
+    """BASELINE.json configs[1]: 100 000 names self-match @0.8, float32 on the GPU side is NOT used — the reference
+    default float64 — every pair against the CPU port."""
+    import bench_cpu
+    from oracle import pipeline as P
+    from string_grouper_b200 import StringGrouper, _device as D
+    n = 100_000
+    names = make_names(n, seed=0)
+    sg = StringGrouper(pd.Series(names)).fit()
+    m, d, _ = P.tf_idf_matrices(names)
+    C = P.build_matches(m, d, P.guess_blocks(n, n), 20, 0.8, _threads())
+    ml = P.matches_list(P.symmetrize_fast(C))
+    job = {"rows": n, "c_indptr": C.indptr.astype(np.int64), "c_indices": C.indices, "c_data": C.data,
+           "row": ml.master_side.to_numpy(), "col": ml.dupe_side.to_numpy(), "score": ml.similarity.to_numpy()}
+    A, _ = sg._get_tf_idf_matrices()
+    pre = D.cossim_topn(A, A, 20, 0.8).host_triples()
+    got = sg._matches_list
+    par = bench_cpu.compare(job, pre, (got.master_side.to_numpy(), got.dupe_side.to_numpy(), got.similarity.to_numpy()))
+    assert par["ok"] and par["match_list"]["pairs_ref"] > 500_000, par
+
+
+def test_config4_shape_two_series_all_pairs_equal_cpu_port():
+    """BASELINE.json configs[3] shape (master x duplicates, min_similarity 0.7) at 400k x 150k: every pair."""
+    from oracle import pipeline as P
+    from parity import compare_triples, csr_triples, row_cutoffs
     from string_grouper_b200 import StringGrouper
     base = make_names(480_000, seed=3)
     master = pd.Series(base[:400_000])
@@ -85,12 +120,36 @@ def test_two_series_large_sampled_rows_equal_oracle():
     assert np.bincount(r).max() <= 20 and c.max() < len(dupes)
     A, B = sg._get_tf_idf_matrices()
     fa, fb = A.to_scipy(), B.to_scipy()
-    rows = np.sort(np.random.default_rng(1).choice(len(master), size=1500, replace=False))
-    ref = sp_matmul_topn(fa[rows], fb.T.tocsr(), top_n=20, threshold=0.7, sort=True, n_threads=16)
-    sel = np.isin(r, rows)
-    pos = np.searchsorted(rows, r[sel])
-    cut = row_cutoffs(ref.indptr, ref.data, 20, len(rows))
-    rr = np.repeat(np.arange(len(rows)), np.diff(ref.indptr))
-    st = compare_triples((rr, ref.indices, ref.data), (pos, c[sel], s[sel]), len(dupes), 0.7, tol=1e-9,
-                         cutoff_row=cut, label="400k x 150k sample")
-    assert st["common"] >= 0.97 * st["pairs_ref"] and st["pairs_ref"] > 500
+    ref = P.build_matches(fa, fb, P.guess_blocks(len(master), len(dupes)), 20, 0.7, _threads())
+    cut = row_cutoffs(ref.indptr, ref.data, 20, len(master))
+    st = compare_triples(csr_triples(ref), (r, c, s), len(dupes), 0.7, tol=1e-9, cutoff_row=cut,
+                         label="400k x 150k")
+    assert st["common"] >= 0.97 * st["pairs_ref"] and st["pairs_ref"] > 100_000
+
+
+def test_config5_shape_groups_equal_cpu_port():
+    """BASELINE.json configs[4] shape: group_similar_strings @0.85 end to end (fit + dedupe) at 250k names against the
+    CPU port: match list, then the reference's _deduplicate restated (oracle/pipeline.deduplicate) on the CPU list."""
+    import bench_cpu
+    from oracle import pipeline as P
+    from string_grouper_b200 import StringGrouper
+    n = 250_000
+    names = pd.Series(make_names(n, seed=5), name="name")
+    for rep in ("centroid", "first"):
+        sg = StringGrouper(names, min_similarity=0.85, group_rep=rep).fit()
+        got = sg.get_groups()
+        if rep == "centroid":
+            A, _ = sg._get_tf_idf_matrices()
+            full = A.to_scipy()
+            C = P.build_matches(full, full, P.guess_blocks(n, n), 20, 0.85, _threads())
+            ml = P.matches_list(P.symmetrize_fast(C))
+            mine = sg._matches_list
+            same_list = (len(ml) == len(mine) and np.array_equal(ml.master_side.to_numpy(), mine.master_side.to_numpy())
+                         and np.array_equal(ml.dupe_side.to_numpy(), mine.dupe_side.to_numpy()))
+        want = P.deduplicate(ml, n, rep)
+        have = got["group_rep_index"].to_numpy()
+        if same_list:
+            assert np.array_equal(have, want), rep
+        else:       # top-n ties inside clusters of identical names may move a pair: the groups still have to agree almost everywhere
+            assert (have != want).mean() < 0.002, rep
+        assert (have != np.arange(n)).sum() > 10_000
