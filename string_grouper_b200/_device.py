@@ -180,11 +180,26 @@ class DeviceCSR:
     def toarray(self):
         return self.to_scipy().toarray()
 
+    def __getitem__(self, key):
+        return self.to_scipy()[key]
+
+    def __matmul__(self, other):
+        return self.to_scipy() @ (other.to_scipy() if hasattr(other, "to_scipy") else other)
+
     def __getattr__(self, name):
-        # anything else scipy offers (indptr, data, T, multiply, ...) comes from the host copy
-        if name.startswith("_") or name.startswith("d_"):
-            raise AttributeError(name)
-        return getattr(self.to_scipy(), name)
+        # the scipy face: only the attributes below materialise the host copy (a typo or a probing hasattr() must not
+        # trigger a device-to-host copy of the whole matrix)
+        if name in _SCIPY_CSR_ATTRS:
+            return getattr(self.to_scipy(), name)
+        raise AttributeError("%s has no attribute %r" % (type(self).__name__, name))
+
+
+# what callers of StringGrouper._get_tf_idf_matrices / _build_matches use on the returned scipy matrices
+_SCIPY_CSR_ATTRS = frozenset([
+    "indptr", "indices", "data", "T", "transpose", "multiply", "dot", "tocsr", "tocsc", "tocoo", "tolil", "todense",
+    "nonzero", "sum", "max", "min", "mean", "getrow", "getcol", "diagonal", "astype", "copy", "getnnz", "has_sorted_indices",
+    "sort_indices", "sorted_indices", "format", "ndim", "count_nonzero", "power", "maximum", "minimum", "A", "todok",
+    "eliminate_zeros", "sum_duplicates", "asformat", "conj", "conjugate", "getH", "setdiag", "trace", "tobsr", "todia"])
 
 
 def as_device_csr(m):
@@ -352,9 +367,24 @@ class DeviceMatches:
         return self.to_scipy().toarray()
 
     def __getattr__(self, name):
-        if name.startswith("_") or name.startswith("d_"):
-            raise AttributeError(name)
-        return getattr(self.to_scipy(), name)
+        if name in _SCIPY_CSR_ATTRS:
+            return getattr(self.to_scipy(), name)
+        raise AttributeError("%s has no attribute %r" % (type(self).__name__, name))
+
+    # operators scipy matrices answer; they materialise the host copy like the attributes above
+    def __getitem__(self, key):
+        return self.to_scipy()[key]
+
+    def __matmul__(self, other):
+        return self.to_scipy() @ other
+
+    def __sub__(self, other):
+        return self.to_scipy() - (other.to_scipy() if hasattr(other, "to_scipy") else other)
+
+    def __ne__(self, other):
+        return self.to_scipy() != (other.to_scipy() if hasattr(other, "to_scipy") else other)
+
+    __hash__ = object.__hash__
 
 
 def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):

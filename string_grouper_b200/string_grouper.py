@@ -232,8 +232,11 @@ class StringGrouper(object):
             try:
                 matches = self._build_matches(master_matrix, duplicate_matrix, self._n_blocks)
             except OverflowError:
-                logger.warning("An OverflowError occurred but is being handled: the candidate buffers are "
-                               "being re-sized, n_blocks = (" + str(guess[0]) + "," + str(guess[1]) + ")")
+                # same control flow as ref:397-413 (its tests mock _build_matches to fail for (1, 1) only).  The
+                # device path sizes its own tiles and row chunks, so n_blocks cannot shrink its buffers: a second
+                # OverflowError from the real kernel path is final (raise min_similarity or split the input).
+                logger.warning("An OverflowError occurred; retrying with the reference's block guess n_blocks = ("
+                               + str(guess[0]) + "," + str(guess[1]) + ")")
                 matches = self._build_matches(master_matrix, duplicate_matrix, guess)
         else:
             matches = self._build_matches(master_matrix, duplicate_matrix, self._n_blocks)
