@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=663_000)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU whole job (parity + cpu_baseline)")
+    ap.add_argument("--no-aux", action="store_true", help="multi-GPU: skip the two-Series sharded-K1 run")
+    ap.add_argument("--aux-master", type=int, default=2_000_000)
+    ap.add_argument("--aux-duplicates", type=int, default=400_000)
     args = ap.parse_args()
 
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -278,9 +281,53 @@ def main():
                              "rank(s)" % int(flag.item()))
         del S1
 
+    # ---- multi-GPU only: one two-Series run that takes the sharded-K1 path (BASELINE.json configs[3] shape) ----
+    aux_two_series = None
+    if world > 1 and not args.no_aux:
+        n_m, n_d = args.aux_master, args.aux_duplicates
+        base = make_names(n_m + int(0.6 * n_d), seed=1)
+        master2 = pd.Series(base[:n_m])
+        dupes2 = pd.Series(base[n_m - (n_d - int(0.6 * n_d)):])          # 40 % of the duplicates are master rows
+        del base
+        os.environ["SG_B200_SHARD_VECTORISE"] = "1"      # K1 sharded: df all-reduce + all-gather of the duplicate CSR
+        D.TIME_KERNELS = True
+        walls = []
+        for rep in range(2):                             # warm-up + one timed run
+            barrier()
+            t0 = time.perf_counter()
+            sg2 = api.StringGrouper(master2, dupes2, min_similarity=0.7)
+            sg2.fit()
+            out2 = sg2.get_matches()
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        D.TIME_KERNELS = False
+        os.environ.pop("SG_B200_SHARD_VECTORISE", None)
+        st2 = sg2._last_stats
+        mine = {"wall_s": walls[-1], "k2_candidates_ms": sum(a.elapsed_time(b) for a, b in st2.get("candidate_events", [])),
+                "phases_ms": {k: round(v, 2) for k, v in D.phases_ms(st2).items()},
+                "sharded_vectorise": bool(st2.get("sharded_vectorise")), "local_nnz": int(st2.get("nnz", 0))}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        t_aux = torch.tensor([walls[-1]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_aux, op=dist.ReduceOp.MAX)
+        n_match = len(sg2._matches_list)
+        aux_two_series = {
+            "workload": "match_strings(master %d, duplicates %d) min_similarity 0.7, K1 sharded over the ranks (df table "
+                        "all-reduce, duplicate-matrix CSR all-gather over NVLink), left rows = this rank's master block"
+                        % (n_m, n_d),
+            "wall_s_max_over_ranks": float(t_aux.item()), "matches": int(n_match),
+            "pairs_per_s": n_match / float(t_aux.item()),
+            "nccl_bytes_per_rank": {"df_allreduce": 4 * (1 << 21),
+                                    "duplicate_csr_allgather": int(16 * sum(p["local_nnz"] for p in per_rank) * n_d / (n_m + n_d)),
+                                    "match_list_allgather": 16 * int(n_match)},
+            "per_rank": per_rank}
+        del sg2, out2, master2, dupes2
+
     # ---- end to end through the public API ("e2e") ----
     e2e_s, e2e_rows, h2d, d2h = [], 0, 0, 0
     e2e_parts = {}
+    if world > 1:
+        os.environ["SG_B200_RESULT"] = "rank0"       # the match list / DataFrame is materialised on rank 0 only
     for step in range(args.warmup + args.steps):
         flush.zero_()
         barrier()
@@ -303,6 +350,14 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = e2e_rows / (float(t_e2e.item()) / args.steps)
+    # the same call on an object-dtype Series (pandas < 3 users): ingest converts to Arrow first (one extra pass)
+    obj_series = series.astype(object)
+    barrier()
+    t0 = time.perf_counter()
+    api.StringGrouper(obj_series).fit().get_matches()
+    torch.cuda.synchronize()
+    e2e_object_s = time.perf_counter() - t0
+    del obj_series
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel chain (K2 candidates) ----
@@ -325,20 +380,21 @@ def main():
     n_loc = hi - lo
     streamed = None
     if st.get("kernel") == "tiles":
+        # bytes the three launches move, from the kernel's own counters (pairs, postings) and the array shapes:
         T = int(st["n_tiles"])
-        mask_words = (T + 63) // 64 * 2
-        kept = int(st.get("features_kept") or 0)
+        Tp = (T + 63) // 64 * 64
+        pairs_w, post_w = int(st["pairs_walked"]), int(st["postings_walked"])
+        feats_per_row = nnz_a_local / max(n_loc, 1)              # upper bound of the kept features per row
         streamed = {
-            "postings_bytes": 4 * int(st["postings_walked"]),                       # shared-memory reads of staged blobs
-            "left_rows_bytes": int(st["pairs_walked"]) * (16 + 8 * max(1, round(nnz_a_local / max(n_loc, 1)))),
-            "survivor_mask_bytes": 2 * 4 * mask_words * n_loc + 4 * T * n_loc // 32 * 32 // 32,
-            "filter_maxw_bytes": 2 * (T + 63) // 64 * 64 * nnz_a_local,             # fp16 block maxima per kept feature
-            "pack_bytes": 24 * nnz_a_local,
+            "postings_bytes": 4 * post_w,                          # shared-memory reads of the TMA-staged tile blobs
+            "left_rows_bytes": int(pairs_w * (16 + 8 * feats_per_row)),   # row record + {feature, weight} per pair (L2)
+            "survivor_mask_bytes": 4 * (Tp // 32) * n_loc + 4 * T * n_loc,  # filter writes it once, every tile reads its word column
+            "filter_block_maxima_bytes": 2 * Tp * nnz_a_local,     # fp16 block maximum per (kept feature, tile) (L2)
+            "pack_left_bytes": 24 * nnz_a_local,
             "candidate_bytes": 8 * int(st["n_candidates"]),
-        }
-        streamed["total"] = int(sum(streamed.values()))
-        streamed["pairs_walked"] = int(st["pairs_walked"])
-        streamed["postings_walked"] = int(st["postings_walked"])
+            "note": "upper bounds where the kept-feature count is needed (the pruned rows hold fewer features)"}
+        streamed["total"] = int(sum(v for v in streamed.values() if isinstance(v, int)))
+        streamed["pairs_walked"], streamed["postings_walked"] = pairs_w, post_w
     traffic = pipe = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and world == 1:      # the ncu capture is a 1-GPU launch over all rows
@@ -403,10 +459,13 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "s_per_step": float(np.mean(e2e_s)), "s_each_step": [round(x, 4) for x in e2e_s],
-                    "rows": e2e_rows, "last_step_parts": e2e_parts},
+                    "rows": e2e_rows, "last_step_parts": e2e_parts,
+                    "input": "Arrow-backed pandas `str` Series (zero-copy ingest); object dtype: `object_dtype_s`",
+                    "object_dtype_s": e2e_object_s,
+                    "result": "every rank" if world == 1 else "rank 0 only (SG_B200_RESULT=rank0)"},
             "gpu_launches": launches // args.steps,
             "phases_ms": {"rank%d" % r: p for r, p in enumerate(phases_all)},
-            "shard_check": shard_check,
+            "shard_check": shard_check, "aux_two_series": aux_two_series,
             "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:

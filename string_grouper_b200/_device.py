@@ -70,9 +70,16 @@ def _empty(n, dtype, device):
     return torch().empty(max(int(n), 1), dtype=dtype, device=device)
 
 
+TIME_KERNELS = False      # bench.py: record CUDA events for the phases of every product (also through the public API)
+
+
+def _timed(stats):
+    return stats is not None and (stats.get("time_kernels") or TIME_KERNELS)
+
+
 def mark(stats, name):
     """Phase boundary for bench.py `phases_ms`: a CUDA event on the current stream when stats["time_kernels"] is set."""
-    if stats is not None and stats.get("time_kernels"):
+    if _timed(stats):
         ev = torch().cuda.Event(enable_timing=True)
         ev.record()
         stats.setdefault("marks", []).append((name, ev))
@@ -608,11 +615,11 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         for attempt in range(3):
             cand_row = _empty(cap, t.int32, dev)
             cand_col = _empty(cap, t.int32, dev)
-            if stats is not None and stats.get("time_kernels"):
+            if _timed(stats):
                 ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                 ev0.record()
             launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap)
-            if stats is not None and stats.get("time_kernels"):
+            if _timed(stats):
                 ev1.record()
                 stats.setdefault("candidate_events", []).append((ev0, ev1))
             head = counters[:4].cpu().numpy()
