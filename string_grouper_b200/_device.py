@@ -36,7 +36,7 @@ CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            
 # also the general path: negative values, norms above 1, near-zero thresholds)
 K2_KERNEL = os.environ.get("SG_B200_KERNEL", "tiles").lower()
 TILE_MARGIN = 2e-5               # fp32 arithmetic of thresholds / norms and the f64 -> f32 copy of the values
-TILE_MARGIN_PER_FEATURE = 3.1e-5  # a_q * w_q / 2^30 vs a * w: both weights rounded to nearest 2^-15 (<= 2^-15 + 2^-32)
+TILE_MARGIN_PER_FEATURE = 6.2e-5  # (a_q * w_q) >> 15 vs a * w: weights rounded to nearest 2^-15, the product truncated to 2^-15
 TILE_WARPS = int(os.environ.get("SG_B200_TILE_WARPS", "8"))
 SELECT_MODE = os.environ.get("SG_B200_SELECT", "rows").lower()      # "rows" (per-row ranking) | "sort" (global sorts)
 
@@ -488,7 +488,11 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         if tiles["stage_bytes"] is None:
             tiles["stage_bytes"] = int(tiles["maxima"][0].item())       # one read-back per right matrix
         smem_optin = t.cuda.get_device_properties(dev).shared_memory_per_block_optin
-        if int(L.sg_tiles_smem_bytes(tiles["stage_bytes"], TILE_WARPS)) > smem_optin:
+        # one CTA per SM: the staged tile + 21 KB per warp (32 lane-private accumulator columns); fewer warps when the
+        # tiles of this matrix are large
+        tile_warps = next((w for w in (8, 6, 4) if w <= TILE_WARPS and
+                           int(L.sg_tiles_smem_bytes(tiles["stage_bytes"], w)) <= smem_optin), None)
+        if tile_warps is None:
             use_tiles, tiles = False, None          # a tile's index does not fit shared memory: row kernel
     if use_tiles:
         margin = TILE_MARGIN * max(scale, 1.0)
@@ -503,7 +507,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     # rows stream the same buckets, and the rows of a column tile have similar heavy norms (tight per-tile bound)
     if use_tiles:
         hrank, perm_b, _ = right_order(B)
-        tile_w, warps, T, tile_bound = tiles["W"], TILE_WARPS, tiles["T"], tiles["bound"]
+        tile_w, warps, T, tile_bound = tiles["W"], tile_warps, tiles["T"], tiles["bound"]
         tiles_per_group = 0
         lpack = _empty(2 * A.d_indices.numel(), t.int32, dev)
         mask_words = int(L.sg_tiles_mask_words(n_right))

@@ -260,67 +260,75 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
                    const uint32_t *__restrict__ maxw_h, int Tp, int64_t T, const float *__restrict__ tile_bound,
                    uint32_t *__restrict__ mask, int64_t mask_stride) {
     __shared__ uint32_t buf[FL_WORDS][FL_RANKS + 1];
+    constexpr int RPW = FL_RANKS / FL_WARPS;          // ranks per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rank0 = (int64_t)blockIdx.x * FL_RANKS;
     const int n_words = Tp >> 5;
     const int half_tp = Tp >> 1;
+    // the warp's ranks: kept features in registers (one per lane)
+    int nf[RPW], f0[RPW];
+    float thr_r[RPW], xp[RPW], slack[RPW];
+    __half2 a2[RPW];
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+        const int64_t r = rank0 + warp * RPW + ri;
+        nf[ri] = 0; f0[ri] = 0; thr_r[ri] = 0.f; xp[ri] = 0.f;
+        a2[ri] = __float2half2_rn(0.f);
+        if (r < n_ranks) {
+            const int4 info = rowinfo[r];
+            nf[ri] = info.y;
+            thr_r[ri] = __int_as_float(info.z);
+            xp[ri] = __int_as_float(info.w);
+            if (lane < info.y) {
+                const int2 fa = lpack[(int64_t)info.x + lane];
+                f0[ri] = fa.x;
+                // rounded up: the bound must not fall short
+                a2[ri] = __half2half2(__float2half_ru((float)fa.y * (1.f / TL_FIX)));
+            }
+        }
+        const int nk = nf[ri] < 32 ? nf[ri] : 32;
+        slack[ri] = 5e-4f * (float)nk + 1e-4f;        // fp16 arithmetic of the bound
+    }
     for (int w0 = 0; w0 < n_words; w0 += FL_WORDS) {
         const int w1 = w0 + FL_WORDS < n_words ? w0 + FL_WORDS : n_words;
-        for (int ri = 0; ri < FL_RANKS / FL_WARPS; ++ri) {
-            const int rr = warp * (FL_RANKS / FL_WARPS) + ri;
-            const int64_t r = rank0 + rr;
-            int nf = 0;
-            float thr_r = 0.f, xp = 0.f;
-            int f0 = 0;
-            __half2 a2 = __float2half2_rn(0.f);
-            if (r < n_ranks) {
-                const int4 info = rowinfo[r];
-                nf = info.y;
-                thr_r = __int_as_float(info.z);
-                xp = __int_as_float(info.w);
-                if (lane < nf) {
-                    const int2 fa = lpack[(int64_t)info.x + lane];
-                    f0 = fa.x;
-                    // rounded up: the bound must not fall short
-                    a2 = __half2half2(__float2half_ru((float)fa.y * (1.f / TL_FIX)));
-                }
-            }
-            const int nk = nf < 32 ? nf : 32;
-            const float slack = 5e-4f * (float)nk + 1e-4f;    // fp16 arithmetic of the bound
-            for (int wd = w0; wd < w1; wd += 2) {
-                const int tb = wd << 5;                       // first tile of the batch
+        // batches outermost: the 32 neighbouring ranks of the CTA (similar rows: mostly the same features) read the same
+        // block-maxima lines within a short time, so most of these loads hit L1 instead of L2
+        for (int wd = w0; wd < w1; wd += 2) {
+            const int tb = wd << 5;                       // first tile of the batch
+            const int t0 = tb + 2 * lane;
+            const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
+            const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
+#pragma unroll
+            for (int ri = 0; ri < RPW; ++ri) {
                 unsigned m_even = 0, m_odd = 0;
-                const int t0 = tb + 2 * lane;
-                if (nf > 32) {                                // more kept features than lanes: every tile is walked
+                if (nf[ri] > 32) {                        // more kept features than lanes: every tile is walked
                     m_even = __ballot_sync(FULL, t0 < T);
                     m_odd = __ballot_sync(FULL, t0 + 1 < T);
-                } else if (nf > 0) {
+                } else if (nf[ri] > 0) {
+                    const int nk = nf[ri];
                     __half2 ub2 = __float2half2_rn(0.f);
-                    const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
-                    // eight block-maxima loads in flight per lane (the table is L2-resident, the loop is latency-bound)
-                    for (int k0 = 0; k0 < nk; k0 += 8) {
+                    for (int k0 = 0; k0 < nk; k0 += 8) {      // eight loads in flight per lane
                         uint32_t m[8];
                         __half2 ak[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int kk = k0 + j;
-                            const int fk = __shfl_sync(FULL, f0, kk & 31);
-                            ak[j] = __shfl_sync(FULL, a2, kk & 31);
+                            const int fk = __shfl_sync(FULL, f0[ri], kk & 31);
+                            ak[j] = __shfl_sync(FULL, a2[ri], kk & 31);
                             m[j] = kk < nk ? mrow[(int64_t)fk * half_tp] : 0u;
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) ub2 = __hfma2(ak[j], *reinterpret_cast<const __half2 *>(&m[j]), ub2);
                     }
                     const float2 ub = __half22float2(ub2);
-                    const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
-                    const float thr0 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.x, thr_r), 0.f) : thr_r;
-                    const float thr1 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.y, thr_r), 0.f) : thr_r;
-                    m_even = __ballot_sync(FULL, t0 < T && ub.x + slack > thr0);
-                    m_odd = __ballot_sync(FULL, t0 + 1 < T && ub.y + slack > thr1);
+                    const float thr0 = xp[ri] > 0.f ? fmaxf(fmaf(-xp[ri], tb2.x, thr_r[ri]), 0.f) : thr_r[ri];
+                    const float thr1 = xp[ri] > 0.f ? fmaxf(fmaf(-xp[ri], tb2.y, thr_r[ri]), 0.f) : thr_r[ri];
+                    m_even = __ballot_sync(FULL, t0 < T && ub.x + slack[ri] > thr0);
+                    m_odd = __ballot_sync(FULL, t0 + 1 < T && ub.y + slack[ri] > thr1);
                 }
                 if (lane == 0) {
-                    buf[wd - w0][rr] = m_even;
-                    buf[wd - w0 + 1][rr] = m_odd;
+                    buf[wd - w0][warp * RPW + ri] = m_even;
+                    buf[wd - w0 + 1][warp * RPW + ri] = m_odd;
                 }
             }
         }
@@ -376,12 +384,31 @@ __device__ __forceinline__ uint32_t lds32_if(uint32_t a, bool pred) {
     return v;
 }
 
-constexpr int TL_SW = 16;                           // lanes per (left row, tile) pair: a warp works on 32 / TL_SW pairs at once
-constexpr int TL_G = 32 / TL_SW;
-// per warp: one accumulator tile per pair group, 256 start-flag words, 32 bucket records, the candidate buffer
-constexpr int TL_WARP_BYTES2 = TL_G * TL_W * 4 + 256 * 4 + 32 * 8 + TL_CBUF * 8;
-constexpr int tl_min_ctas(int nw) { return nw == 16 ? 1 : 2; }
-__host__ __device__ constexpr int tl_list(int nw) { return nw * 256; }     // survivor ranks per scan round
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("{ .reg .u16 h; cvt.u16.u32 h, %1; st.shared.u16 [%0], h; }" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// the shared-window base as a value the compiler cannot re-derive (it would recompute it from the CTA id per use)
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(x));
+    return x;
+}
+
+// Thread-per-pair layout.  A (left row, tile) pair is tiny — about 13 kept features, 70 postings, 2 columns over the
+// threshold — so warp-collective processing (prefix sums, owner search, votes per 32 postings) costs more than the work.
+// Here every LANE owns one pair: its 256 partial scores are 16-bit fixed point (2^-15 units) in a lane-private column
+// of the warp's accumulator block (acc[col][lane]: conflict-free, no atomics), its features arrive by cp.async into a
+// lane-private row of a staging block, its buckets are found and walked serially.  32 pairs advance per warp step.
+constexpr int TP_FS = 16;                           // features staged per pair and round (rows with more: more rounds)
+constexpr int TP_FSTRIDE = TP_FS + 1;               // 8-byte entries per pair row, padded: lane = pair access is conflict-free
+constexpr int TP_ACC_BYTES = TL_W * 32 * 2;         // 16 KB: 256 columns x 32 pairs x u16
+constexpr int TL_WARP_BYTES2 = TP_ACC_BYTES + 32 * TP_FSTRIDE * 8 + TL_CBUF * 8;
+constexpr int tl_min_ctas(int) { return 1; }
+__host__ __device__ constexpr int tl_list(int nw) { return nw * 256 + nw * 32; }     // survivor ranks held per round
+constexpr float TP_FIX = 32768.f;
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, tl_min_ctas(NW))
@@ -401,17 +428,15 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
     uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + TL_HEAD_BYTES);
     unsigned char *stage = smem + TL_HEAD_BYTES + tl_list(NW) * 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / TL_SW, gl = lane % TL_SW;              // pair group of the lane, lane inside the group
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t smem_s = opaque(smem_u32(smem));
     const uint32_t stage_s = smem_s + TL_HEAD_BYTES + tl_list(NW) * 4;
     const uint32_t warp_s = stage_s + stage_bytes + warp * TL_WARP_BYTES2;
-    const uint32_t acc_s = warp_s + g * (TL_W * 4);                         // this group's accumulator tile
-    const uint32_t flags_s = warp_s + TL_G * TL_W * 4 + g * (1024 / TL_G);  // this group's start-flag words
-    const uint32_t dk_s = warp_s + TL_G * TL_W * 4 + 1024 + g * (TL_SW * 8);
-    const uint32_t cbuf_s = warp_s + TL_G * TL_W * 4 + 1024 + 256;
+    const uint32_t acc_s = warp_s + lane * 2;                               // this lane's column of partial scores
+    const uint32_t feat_s = warp_s + TP_ACC_BYTES + lane * (TP_FSTRIDE * 8);  // this lane's feature / bucket row
+    const uint32_t cbuf_s = warp_s + TP_ACC_BYTES + 32 * TP_FSTRIDE * 8;
     int ccount = 0;
-    for (int c = lane; c < (TL_G * TL_W * 4 + 1024) / 16; c += 32) sts128z(warp_s + c * 16);
+    for (int c = lane; c < TP_ACC_BYTES / 16; c += 32) sts128z(warp_s + c * 16);
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         *s_count = 0;
@@ -420,7 +445,7 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
 
     const unsigned long long n_items = (unsigned long long)T * (unsigned long long)n_seg;
     unsigned parity = 0;
-    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added (per lane group)
+    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added by this lane
 
     // buffered candidates -> global list (one atomic per flush)
     auto flush = [&]() {
@@ -474,142 +499,129 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         const int bit = (t & 63) >> 1;
         bool staged = false;
 
-        for (int64_t base = rank_lo; base < rank_hi; base += (int64_t)NW * 256) {
-            // ---- scan round: every warp tests 256 ranks (eight coalesced mask words in flight) and appends the
-            // survivors to the CTA's list.  Survivors cluster in rank order (similar rows are neighbours), so the list
-            // is dealt out to the warps round-robin afterwards.
-            const int64_t gbase = base + ((int64_t)warp << 8);
-            uint32_t wsv[8];
+        int64_t base = rank_lo;
+        while (base < rank_hi) {
+            // ---- scan rounds: every warp tests 256 ranks per round (eight coalesced mask words in flight) and appends
+            // the survivors to the CTA's list, until the list holds a full 32-pair chunk for every warp
+            int count = 0;
+            for (;;) {
+                const int64_t gbase = base + ((int64_t)warp << 8);
+                uint32_t wsv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int64_t r = gbase + j * 32 + lane;
-                wsv[j] = r < rank_hi ? mrow[r] : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
-                if (sv) {
-                    int pos = 0;
-                    if (lane == 0) pos = atomicAdd(s_count, __popc(sv));
-                    pos = __shfl_sync(FULL, pos, 0);
-                    if ((sv >> lane) & 1u) s_list[pos + __popc(sv & lt_mask)] = (uint32_t)(gbase + j * 32 + lane);
+                for (int j = 0; j < 8; ++j) {
+                    const int64_t r = gbase + j * 32 + lane;
+                    wsv[j] = r < rank_hi ? mrow[r] : 0u;
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
+                    if (sv) {
+                        int pos = 0;
+                        if (lane == 0) pos = atomicAdd(s_count, __popc(sv));
+                        pos = __shfl_sync(FULL, pos, 0);
+                        if ((sv >> lane) & 1u) s_list[pos + __popc(sv & lt_mask)] = (uint32_t)(gbase + j * 32 + lane);
+                    }
+                }
+                base += (int64_t)NW * 256;
+                __syncthreads();
+                count = *reinterpret_cast<volatile int *>(s_count);
+                if (count >= NW * 32 || base >= rank_hi) break;
+                __syncthreads();          // everybody has read the count before the next round appends
             }
-            __syncthreads();
-            const int count = *reinterpret_cast<volatile int *>(s_count);
             if (count > 0) {
                 if (!staged) {
                     mbar_wait(mbar, parity);
                     staged = true;
                 }
-                // ---- this warp's pairs: TL_G list entries at a time (one per lane group), dealt round-robin over the
-                // warps; the row record of the next entry and its first features are fetched one step ahead
-                int i = warp * TL_G + g;
-                int r_c = 0, r_n = 0;
-                int4 info_c = make_int4(0, 0, 0, 0), info_n = info_c;
-                int2 fa_c = make_int2(0, 0), fb_c = fa_c;
-                if (i < count) {
-                    r_c = (int)s_list[i];
-                    info_c = rowinfo[r_c];
-                    if (gl < info_c.y) fa_c = lpack[(int64_t)info_c.x + gl];
-                    if (gl + TL_SW < info_c.y) fb_c = lpack[(int64_t)info_c.x + gl + TL_SW];
-                }
-                if (i + NW * TL_G < count) {
-                    r_n = (int)s_list[i + NW * TL_G];
-                    info_n = rowinfo[r_n];
-                }
-                for (int i0 = warp * TL_G; i0 < count; i0 += NW * TL_G) {
-                    int2 fa_n = make_int2(0, 0), fb_n = fa_n;
-                    if (gl < info_n.y) fa_n = lpack[(int64_t)info_n.x + gl];
-                    if (gl + TL_SW < info_n.y) fb_n = lpack[(int64_t)info_n.x + gl + TL_SW];
-                    int r_nn = 0;
-                    int4 info_nn = make_int4(0, 0, 0, 0);
-                    if (i + 2 * NW * TL_G < count) {
-                        r_nn = (int)s_list[i + 2 * NW * TL_G];
-                        info_nn = rowinfo[r_nn];
+                // ---- chunks of 32 consecutive list entries (neighbouring ranks: similar rows, similar work), dealt
+                // round-robin to the warps; lane = pair
+                for (int c0 = warp * 32; c0 < count; c0 += NW * 32) {
+                    const int idx = c0 + lane;
+                    int r = 0;
+                    int4 info = make_int4(0, 0, 0, 0);
+                    if (idx < count) {
+                        r = (int)s_list[idx];
+                        info = rowinfo[r];
                     }
-                    // ---- TL_G (left row, tile) pairs, one per lane group (nf == 0: no pair in this group)
-                    const int nf = info_c.y;
-                    const float thr_r = __int_as_float(info_c.z);
-                    const float xp = __int_as_float(info_c.w);
+                    const int nf = info.y;                      // 0: no pair in this lane
+                    const float thr_r = __int_as_float(info.z);
+                    const float xp = __int_as_float(info.w);
                     const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;
-                    const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));
-                    if (gl == 0 && nf > 0) ++n_pairs;
-                    bool touched = false;
-                    for (int fb = 0; __any_sync(FULL, fb < nf); fb += TL_SW) {
-                        int2 e_fa = fb == 0 ? fa_c : fb_c;
-                        const bool active = fb + gl < nf;
-                        if (fb >= 2 * TL_SW) {           // rows with more than 2 * TL_SW kept features: fetched on demand
-                            e_fa = make_int2(0, 0);
-                            if (active) e_fa = lpack[(int64_t)info_c.x + fb + gl];
+                    const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 1.99f) * TP_FIX);
+                    if (nf > 0) ++n_pairs;
+                    for (int fb0 = 0; __any_sync(FULL, fb0 < nf); fb0 += TP_FS) {
+                        // features [fb0, fb0 + TP_FS) of every pair -> the pair's staging row (cp.async: 32 rows in
+                        // flight, no registers); two pairs per step, 16 lanes each
+                        for (int jj = 0; jj < 32; jj += 2) {
+                            const int j = jj + (lane >> 4), k = lane & 15;
+                            const int p0j = __shfl_sync(FULL, info.x, j);
+                            const int nfj = __shfl_sync(FULL, nf, j);
+                            if (fb0 + k < nfj)
+                                cp_async8(warp_s + TP_ACC_BYTES + (j * TP_FSTRIDE + k) * 8, lpack + (int64_t)p0j + fb0 + k);
                         }
-                        // bucket of the lane's feature through the bitmap directory (all loads unconditional: feature
-                        // 0 for idle lanes)
-                        const unsigned f = active ? (unsigned)e_fa.x : 0u;
-                        const uint32_t bmw = lds32(bitmap_s + ((f >> 5) << 2));
-                        const uint32_t pre = lds16(prefix_s + ((f >> 5) << 1));
-                        const uint32_t jb = pre + __popc(bmw & ((1u << (f & 31)) - 1u));
-                        const uint32_t o0 = lds16(off_s + (jb << 1));
-                        const uint32_t o1 = lds16(off_s + (jb << 1) + 2);
-                        const int len = (active && ((bmw >> (f & 31)) & 1u)) ? (int)(o1 - o0) : 0;
-                        // the group's buckets as ONE concatenated list; the owner of a position is the number of bucket
-                        // starts at or before it (start bits + popc)
-                        int incl = len;
-#pragma unroll
-                        for (int o = 1; o < TL_SW; o <<= 1) {
-                            const int up = __shfl_up_sync(FULL, incl, o, TL_SW);
-                            if (gl >= o) incl += up;
-                        }
-                        const int total = __shfl_sync(FULL, incl, TL_SW - 1, TL_SW);
-                        int max_total = total;
-#pragma unroll
-                        for (int o = TL_SW; o < 32; o <<= 1) max_total = max(max_total, __shfl_xor_sync(FULL, max_total, o));
-                        if (max_total == 0) continue;
-                        touched = touched || total > 0;
-                        if (gl == 0) n_walked += (unsigned)total;
-                        const unsigned nz = __ballot_sync(FULL, len > 0);
-                        if (len > 0) {
-                            const int st = incl - len;
-                            const unsigned before = nz & lt_mask & (TL_SW == 32 ? FULL : (((1u << TL_SW) - 1u) << (g * TL_SW)));
-                            sts64(dk_s + __popc(before) * 8, (uint32_t)((int)o0 - st), (uint32_t)e_fa.y);
-                            reds_or(flags_s + ((st >> 5) << 2), 1u << (st & 31));
-                        }
+                        cp_async_wait_all();
                         __syncwarp();
-                        int kb = -1, kb_next = -1;
-                        for (int s0 = 0; s0 < max_total; s0 += TL_SW) {
-                            const int item = s0 + gl;
-                            const uint32_t word = lds32(flags_s + ((item >> 5) << 2));
-                            if ((s0 & 31) == 0) {          // uniform: the step enters a new flag word
-                                kb = kb_next;
-                                kb_next = kb + __popc(word);
+                        // buckets of this lane's features through the bitmap directory, compacted in place
+                        const int myn = nf - fb0 < TP_FS ? nf - fb0 : TP_FS;
+                        int nb = 0;
+                        for (int k = 0; __any_sync(FULL, k < myn); ++k) {
+                            if (k < myn) {
+                                const uint2 fa = lds64(feat_s + k * 8);
+                                const unsigned f = fa.x;
+                                const uint32_t bmw = lds32(bitmap_s + ((f >> 5) << 2));
+                                if ((bmw >> (f & 31)) & 1u) {
+                                    const uint32_t jb = lds16(prefix_s + ((f >> 5) << 1)) + __popc(bmw & ((1u << (f & 31)) - 1u));
+                                    const uint32_t o0 = lds16(off_s + (jb << 1));
+                                    const uint32_t o1 = lds16(off_s + (jb << 1) + 2);
+                                    sts64(feat_s + nb * 8, o0 | ((o1 - o0) << 16), fa.y);
+                                    ++nb;
+                                }
                             }
-                            const bool in = item < total;
-                            const int k = in ? kb + __popc(word & ((2u << (item & 31)) - 1u)) : 0;
-                            const uint2 dd = lds64(dk_s + k * 8);
-                            const uint32_t e = lds32_if(post_s + (((int)dd.x + item) << 2), in);
-                            const uint32_t x = (e >> 16) * dd.y;
-                            const uint32_t cb = e & 0xffffu;
-                            const uint32_t old = atoms_add_if(acc_s + cb, x, in);
-                            const bool crossed = in && old <= thr_c && old + x > thr_c;
+                        }
+                        // walk: one posting per lane and step; products a_q * w_q >> 15 into the lane's own column
+                        int bi = 0;
+                        uint32_t p = 0, pend = 0, aq = 0;
+                        bool done = nb == 0;
+                        for (;;) {
+                            if (!done && p == pend) {
+                                if (bi < nb) {
+                                    const uint2 b = lds64(feat_s + bi * 8);
+                                    ++bi;
+                                    p = b.x & 0xffffu;
+                                    pend = p + (b.x >> 16);
+                                    aq = b.y;
+                                    n_walked += (b.x >> 16);
+                                } else {
+                                    done = true;
+                                }
+                            }
+                            if (__all_sync(FULL, done)) break;
+                            bool crossed = false;
+                            uint32_t cb = 0;
+                            if (!done) {
+                                const uint32_t e = lds32(post_s + (p << 2));
+                                ++p;
+                                const uint32_t x = ((e >> 16) * aq) >> 15;
+                                cb = e & 0xffffu;                              // column * 4
+                                const uint32_t a_addr = acc_s + (cb << 4);     // column * 64 bytes + lane * 2
+                                const uint32_t old = lds16(a_addr);
+                                const uint32_t now = old + x;
+                                sts16(a_addr, now);
+                                crossed = old <= thr_c && now > thr_c;
+                            }
                             const unsigned em = __ballot_sync(FULL, crossed);
                             if (em) {
-                                if (crossed) sts64(cbuf_s + (ccount + __popc(em & lt_mask)) * 8, (uint32_t)r_c, (uint32_t)(col0 + (int)(cb >> 2)));
+                                if (crossed) sts64(cbuf_s + (ccount + __popc(em & lt_mask)) * 8, (uint32_t)r, (uint32_t)(col0 + (int)(cb >> 2)));
                                 ccount += __popc(em);
                                 if (ccount > TL_CBUF - 32) flush();
                             }
                         }
                         __syncwarp();
-                        for (int w = gl; (w << 5) < total; w += TL_SW) sts32(flags_s + (w << 2), 0u);
-                        __syncwarp();
                     }
-                    if (touched) {
-#pragma unroll
-                        for (int c = 0; c < TL_W * 4 / 16 / TL_SW; ++c) sts128z(acc_s + (c * TL_SW + gl) * 16);
-                    }
+                    // clear the warp's accumulator block (contiguous 16 KB)
+#pragma unroll 4
+                    for (int c = 0; c < TP_ACC_BYTES / 16 / 32; ++c) sts128z(warp_s + (c * 32 + lane) * 16);
                     __syncwarp();
-                    r_c = r_n; info_c = info_n; fa_c = fa_n; fb_c = fb_n;
-                    r_n = r_nn; info_n = info_nn;
-                    i += NW * TL_G;
                 }
             }
             __syncthreads();
@@ -621,9 +633,16 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         __syncthreads();      // every warp is done with the staged tile before the next one is copied over it
     }
     flush();
-    if (walk_stats && gl == 0) {
-        atomicAdd(walk_stats, n_pairs);
-        atomicAdd(walk_stats + 1, n_walked);
+    if (walk_stats) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
+            n_walked += __shfl_xor_sync(FULL, n_walked, o);
+        }
+        if (lane == 0) {
+            atomicAdd(walk_stats, n_pairs);
+            atomicAdd(walk_stats + 1, n_walked);
+        }
     }
 }
 
@@ -765,7 +784,8 @@ int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begi
                         unsigned long long *walk_stats, int warps_per_cta, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_ranks <= 0 || n_right <= 0) return SG_OK;
-    if (warps_per_cta != 8 && warps_per_cta != 16) return fail(SG_ERR_INVALID, "warps_per_cta must be 8 or 16");
+    if (warps_per_cta != 4 && warps_per_cta != 6 && warps_per_cta != 8)
+        return fail(SG_ERR_INVALID, "warps_per_cta must be 4, 6 or 8");
     int dev = 0, n_sm = 0, smem_optin = 0;
     SG_CUDA_TRY(cudaGetDevice(&dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -798,7 +818,7 @@ int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begi
             (const TileDesc *)tile_desc, (const unsigned char *)blob, T, bw, tile_bound, perm_b, seg_ranks, n_seg,   \
             cand_row, cand_col, (unsigned long long)cand_cap, cand_count, queue, walk_stats, stage_bytes);           \
     } while (0)
-    if (warps_per_cta == 16) SG_TL_LAUNCH(16); else SG_TL_LAUNCH(8);
+    if (warps_per_cta == 4) SG_TL_LAUNCH(4); else if (warps_per_cta == 6) SG_TL_LAUNCH(6); else SG_TL_LAUNCH(8);
 #undef SG_TL_LAUNCH
     SG_LAUNCH_CHECK();
     return SG_OK;
