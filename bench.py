@@ -376,25 +376,38 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-    # what the launch chain really reads and writes (counted by the kernel itself / from the array sizes)
+    # what the launches really read and write: the (row, tile) pairs that survive the block-max test and the postings of
+    # their buckets are COUNTED by the tile formulation's kernel on the same input (one untimed run; both formulations
+    # apply the same pruning and the same block-max test), the rest follows from the array shapes
     n_loc = hi - lo
+    st_walk = {}
+    D.cossim_topn(A, A, TOP_N, MIN_SIM, row_begin=lo, row_end=hi, stats=st_walk, kernel="tiles")
     streamed = None
-    if st.get("kernel") == "tiles":
-        # bytes the three launches move, from the kernel's own counters (pairs, postings) and the array shapes:
+    if st_walk.get("kernel") == "tiles" and st_walk.get("pairs_walked"):
         T = int(st["n_tiles"])
         Tp = (T + 63) // 64 * 64
-        pairs_w, post_w = int(st["pairs_walked"]), int(st["postings_walked"])
+        pairs_w, post_w = int(st_walk["pairs_walked"]), int(st_walk["postings_walked"])
         feats_per_row = nnz_a_local / max(n_loc, 1)              # upper bound of the kept features per row
-        streamed = {
-            "postings_bytes": 4 * post_w,                          # shared-memory reads of the TMA-staged tile blobs
-            "left_rows_bytes": int(pairs_w * (16 + 8 * feats_per_row)),   # row record + {feature, weight} per pair (L2)
-            "survivor_mask_bytes": 4 * (Tp // 32) * n_loc + 4 * T * n_loc,  # filter writes it once, every tile reads its word column
-            "filter_block_maxima_bytes": 2 * Tp * nnz_a_local,     # fp16 block maximum per (kept feature, tile) (L2)
-            "pack_left_bytes": 24 * nnz_a_local,
-            "candidate_bytes": 8 * int(st["n_candidates"]),
-            "note": "upper bounds where the kept-feature count is needed (the pruned rows hold fewer features)"}
-        streamed["total"] = int(sum(v for v in streamed.values() if isinstance(v, int)))
+        if st.get("kernel") == "tiles":
+            streamed = {
+                "postings_bytes": 4 * post_w,                          # shared-memory reads of the TMA-staged tile blobs
+                "left_rows_bytes": int(pairs_w * (16 + 8 * feats_per_row)),   # row record + {feature, weight} per pair
+                "survivor_mask_bytes": 4 * (Tp // 32) * n_loc + 4 * int(st_walk["n_tiles"]) * n_loc,
+                "filter_block_maxima_bytes": 2 * Tp * nnz_a_local,     # fp16 block maximum per (kept feature, tile)
+                "pack_left_bytes": 24 * nnz_a_local,
+                "candidate_bytes": 8 * int(st["n_candidates"])}
+        else:
+            streamed = {
+                "postings_bytes": 4 * post_w,                          # 4-byte postings of the surviving buckets (L2)
+                "directory_bytes": int(8 * pairs_w * feats_per_row),   # one 8-byte bucket entry per kept feature and pair
+                "filter_block_maxima_bytes": 2 * Tp * nnz_a_local,     # fp16 block maximum per (kept feature, tile) (L2)
+                "left_rows_bytes": 12 * nnz_a_local * max(1, (T + int(st.get("tiles_per_group") or T) - 1)
+                                                          // int(st.get("tiles_per_group") or T)),
+                "candidate_bytes": 8 * int(st["n_candidates"])}
+        streamed["total"] = int(sum(streamed.values()))
         streamed["pairs_walked"], streamed["postings_walked"] = pairs_w, post_w
+        streamed["note"] = ("pairs / postings counted by sg::tile_candidates_kernel on the same input; upper bounds where "
+                            "the kept-feature count is needed (the pruned rows hold fewer features)")
     traffic = pipe = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and world == 1:      # the ncu capture is a 1-GPU launch over all rows
@@ -406,7 +419,7 @@ def main():
     achieved = (bytes_real / (k2_ms / 1e3) / 1e9) if bytes_real else None
     alg_gbps = alg_bytes / (k2_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "K2 candidates chain: sg::pack_left + sg::tile_filter + sg::tile_candidates"
-                if streamed else "sg::cossim_candidates_kernel",
+                if st.get("kernel") == "tiles" else "sg::cossim_candidates_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": k2_ms,
                 "kernel_share_of_step": k2_ms / float(np.mean(step_ms)),

@@ -316,8 +316,9 @@ int sg_topn_select(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_
 /*
  * The same selection without global sorts (csrc/sg_select.cu): the survivors (already strictly above the threshold,
  * counted per row by sg_rescore's `row_cnt`) are bucketed by row; rows of up to 32 survivors are ranked by one warp
- * with a shuffle bitonic network, rows of up to sg_topn_rows_cap() by one CTA in shared memory.  When
- * sg_row_count_max() reports a larger row the caller uses sg_topn_select instead.  Same outputs and tie rule.
+ * with a shuffle bitonic network, rows of up to 512 by one warp in shared memory, longer rows by one CTA in pieces of
+ * sg_topn_rows_cap() with the best top_n carried along.  Valid when sg_row_count_max() <= sg_topn_rows_cap() or
+ * top_n <= sg_topn_rows_cap() / 2; otherwise the caller uses sg_topn_select.  Same outputs and tie rule.
  */
 int sg_topn_rows_cap(void);
 int sg_row_count_max(int64_t n_rows, const int32_t *row_cnt /*[dev]*/, int32_t *out_max /*[dev] 1, zeroed*/,

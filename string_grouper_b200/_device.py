@@ -31,12 +31,13 @@ ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulato
 MAX_CAND_DENSITY = float(os.environ.get("SG_B200_MAX_CAND_DENSITY", "1.5e-3"))   # candidates per (row, column) pair
 MAX_BUCKETS = int(os.environ.get("SG_B200_MAX_BUCKETS", str(400_000_000)))       # directory entries (22 B each)
 CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
-# K2 formulation for L2-normalised non-negative operands: "tiles" = right tiles staged through TMA into shared memory
-# (csrc/sg_tiles.cu, the default), "row" = one warp per left row over L2-resident posting buckets (csrc/sg_cossim.cu,
-# also the general path: negative values, norms above 1, near-zero thresholds)
-K2_KERNEL = os.environ.get("SG_B200_KERNEL", "tiles").lower()
+# K2 formulation: "row" (the default) = one warp per left row over L2-resident posting buckets (csrc/sg_cossim.cu; also
+# the general path: negative values, norms above 1, near-zero thresholds); "tiles" = right tiles staged through TMA into
+# shared memory (csrc/sg_tiles.cu), for L2-normalised non-negative operands.  Measured on B200 at 663k rows the row kernel
+# is the faster one (both are bound by instruction issue at ~340 warp instructions per (row, tile) pair).
+K2_KERNEL = os.environ.get("SG_B200_KERNEL", "row").lower()
 TILE_MARGIN = 2e-5               # fp32 arithmetic of thresholds / norms and the f64 -> f32 copy of the values
-TILE_MARGIN_PER_FEATURE = 6.2e-5  # (a_q * w_q) >> 15 vs a * w: weights rounded to nearest 2^-15, the product truncated to 2^-15
+TILE_MARGIN_PER_FEATURE = 3.1e-5  # a_q * w_q / 2^30 vs a * w: both weights rounded to nearest 2^-15 (<= 2^-15 + 2^-32)
 TILE_WARPS = int(os.environ.get("SG_B200_TILE_WARPS", "8"))
 SELECT_MODE = os.environ.get("SG_B200_SELECT", "rows").lower()      # "rows" (per-row ranking) | "sort" (global sorts)
 
@@ -488,9 +489,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         if tiles["stage_bytes"] is None:
             tiles["stage_bytes"] = int(tiles["maxima"][0].item())       # one read-back per right matrix
         smem_optin = t.cuda.get_device_properties(dev).shared_memory_per_block_optin
-        # one CTA per SM: the staged tile + 21 KB per warp (32 lane-private accumulator columns); fewer warps when the
-        # tiles of this matrix are large
-        tile_warps = next((w for w in (8, 6, 4) if w <= TILE_WARPS and
+        tile_warps = next((w for w in (TILE_WARPS, 8) if w in (8, 16) and
                            int(L.sg_tiles_smem_bytes(tiles["stage_bytes"], w)) <= smem_optin), None)
         if tile_warps is None:
             use_tiles, tiles = False, None          # a tile's index does not fit shared memory: row kernel
@@ -682,7 +681,8 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     out_col = _empty(n_cand, t.int32, dev)
     out_score = _empty(n_cand, t.float64, dev)
     tail = t.zeros(2, dtype=t.int64, device=dev)            # [0] out_nnz, [1] max_row (int32 view)
-    if max_row_cnt <= int(L.sg_topn_rows_cap()) and SELECT_MODE != "sort":
+    rows_cap = int(L.sg_topn_rows_cap())
+    if (max_row_cnt <= rows_cap or top_n <= rows_cap // 2) and SELECT_MODE != "sort":
         # survivors bucketed by row, every row ranked on its own (warp shuffle network / one CTA in shared memory)
         ws_bytes = int(L.sg_topn_select_rows_workspace_bytes(n_cand, n_rows))
         ws = _empty(ws_bytes, t.uint8, dev)
@@ -690,7 +690,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                          _ptr(row_cnt), _ptr(out_indptr), _ptr(out_row), _ptr(out_col),
                                          _ptr(out_score), ctypes.c_void_p(tail.data_ptr()),
                                          ctypes.c_void_p(tail.data_ptr() + 8), _ptr(ws), ws_bytes, _stream()))
-        LAUNCH_COUNTS["select"] += 5
+        LAUNCH_COUNTS["select"] += 6
         if stats is not None:
             stats["select"] = "rows"
     else:

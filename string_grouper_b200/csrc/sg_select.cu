@@ -4,8 +4,9 @@
 // A.3): per left row keep the `top_n` largest scores strictly above the threshold, emit them value-descending
 // (sort=True).  sg_topn_select (sg_cossim.cu) does this with three global radix sorts over all survivors; here the
 // survivors are bucketed by row (the exact re-score has already counted them per row), and every row is ranked on
-// its own: rows of up to 32 survivors (nearly all) by one warp with a shuffle bitonic network, rows of up to
-// SEL_BIG_CAP survivors by one CTA in shared memory.  Rows beyond that are left to sg_topn_select by the caller.
+// its own: rows of up to 32 survivors (nearly all) by one warp with a shuffle bitonic network, rows of up to 512 by
+// one warp in shared memory, longer rows by one CTA (in pieces of SEL_BIG_CAP with the best top_n carried along, which
+// needs top_n <= SEL_BIG_CAP / 2; otherwise the caller uses sg_topn_select).
 //
 // Order: score descending; among EQUAL scores the larger column wins the cut (what the upstream traversal keeps for
 // identical strings) and the survivors of a tie are written in ascending column order — the rule of sg_topn_select.
@@ -108,7 +109,68 @@ sel_rows_small_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restri
     }
 }
 
-// persistent CTAs over the rows with 33 .. SEL_BIG_CAP survivors
+constexpr int SEL_MID_CAP = 512;         // survivors of one row a single warp ranks in shared memory
+constexpr int SEL_MID_WARPS = 8;
+
+// rows with 33 .. SEL_MID_CAP survivors: one warp per row (no block barriers), bitonic network in shared memory
+__global__ void __launch_bounds__(SEL_MID_WARPS * 32)
+sel_rows_mid_kernel(int64_t row_begin, const int64_t *__restrict__ row_start, const int32_t *__restrict__ b_col,
+                    const double *__restrict__ b_score, int top_n, const int64_t *__restrict__ out_indptr,
+                    int32_t *__restrict__ out_row, int32_t *__restrict__ out_col, double *__restrict__ out_score,
+                    const int32_t *__restrict__ big_rows, const int32_t *__restrict__ n_big) {
+    __shared__ uint64_t s_key[SEL_MID_WARPS][SEL_MID_CAP];
+    __shared__ int32_t s_col[SEL_MID_WARPS][SEL_MID_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t *key = s_key[warp];
+    int32_t *col = s_col[warp];
+    const int nb = *n_big;
+    for (int bi = blockIdx.x * SEL_MID_WARPS + warp; bi < nb; bi += gridDim.x * SEL_MID_WARPS) {
+        const int64_t r = big_rows[bi];
+        const int64_t s0 = row_start[r];
+        const int m = (int)(row_start[r + 1] - s0);
+        if (m > SEL_MID_CAP) continue;          // sel_rows_big_kernel
+        int P = 64;
+        while (P < m) P <<= 1;
+        for (int i = lane; i < P; i += 32) {
+            key[i] = i < m ? score_key_desc(b_score[s0 + i]) : ~0ull;
+            col[i] = i < m ? b_col[s0 + i] : -1;
+        }
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < P; i += 32) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const bool up = ((i & k) == 0);
+                        const bool in_order = !sel_before(key[p], col[p], key[i], col[i]);
+                        if (in_order != up) {
+                            const uint64_t tk = key[i]; key[i] = key[p]; key[p] = tk;
+                            const int32_t tc = col[i]; col[i] = col[p]; col[p] = tc;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const int kk = m < top_n ? m : top_n;
+        for (int i = lane; i < kk; i += 32) {
+            const uint64_t kx = key[i];
+            int a = i, b = i + 1;
+            while (a > 0 && key[a - 1] == kx) --a;
+            while (b < kk && key[b] == kx) ++b;
+            const int64_t w = out_indptr[r] + a + (b - 1 - i);
+            uint64_t bits = ~kx;                                    // back to the score
+            bits = (bits >> 63) ? (bits & 0x7fffffffffffffffull) : ~bits;
+            out_row[w] = (int32_t)(r + row_begin);
+            out_col[w] = col[i];
+            out_score[w] = __longlong_as_double((long long)bits);
+        }
+        __syncwarp();
+    }
+}
+
+// rows with more than SEL_MID_CAP survivors: persistent CTAs; a row longer than SEL_BIG_CAP is taken in pieces, the
+// best top_n so far carried along (needs top_n <= SEL_BIG_CAP / 2)
 __global__ void __launch_bounds__(256)
 sel_rows_big_kernel(int64_t row_begin, const int64_t *__restrict__ row_start, const int32_t *__restrict__ b_col,
                     const double *__restrict__ b_score, int top_n, const int64_t *__restrict__ out_indptr,
@@ -121,31 +183,39 @@ sel_rows_big_kernel(int64_t row_begin, const int64_t *__restrict__ row_start, co
         const int64_t r = big_rows[bi];
         const int64_t s0 = row_start[r];
         const int m = (int)(row_start[r + 1] - s0);
-        if (m > SEL_BIG_CAP) continue;          // the caller routes such inputs to sg_topn_select
-        int P = 64;
-        while (P < m) P <<= 1;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            s_key[i] = i < m ? score_key_desc(b_score[s0 + i]) : ~0ull;
-            s_col[i] = i < m ? b_col[s0 + i] : -1;
-        }
-        __syncthreads();
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                    const int p = i ^ j;
-                    if (p > i) {
-                        const bool up = ((i & k) == 0);
-                        const bool in_order = !sel_before(s_key[p], s_col[p], s_key[i], s_col[i]);
-                        if (in_order != up) {
-                            const uint64_t tk = s_key[i]; s_key[i] = s_key[p]; s_key[p] = tk;
-                            const int32_t tc = s_col[i]; s_col[i] = s_col[p]; s_col[p] = tc;
+        if (m <= SEL_MID_CAP) continue;         // sel_rows_mid_kernel
+        int kept = 0;
+        for (int start = 0; start < m;) {
+            const int take = (SEL_BIG_CAP - kept) < (m - start) ? (SEL_BIG_CAP - kept) : (m - start);
+            const int n_now = kept + take;
+            int P = 64;
+            while (P < n_now) P <<= 1;
+            for (int i = kept + threadIdx.x; i < P; i += blockDim.x) {
+                const int q = i - kept;
+                s_key[i] = q < take ? score_key_desc(b_score[s0 + start + q]) : ~0ull;
+                s_col[i] = q < take ? b_col[s0 + start + q] : -1;
+            }
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                        const int p = i ^ j;
+                        if (p > i) {
+                            const bool up = ((i & k) == 0);
+                            const bool in_order = !sel_before(s_key[p], s_col[p], s_key[i], s_col[i]);
+                            if (in_order != up) {
+                                const uint64_t tk = s_key[i]; s_key[i] = s_key[p]; s_key[p] = tk;
+                                const int32_t tc = s_col[i]; s_col[i] = s_col[p]; s_col[p] = tc;
+                            }
                         }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
+            kept = n_now < top_n ? n_now : top_n;       // the best so far, in order, at the front
+            start += take;
         }
-        const int kk = m < top_n ? m : top_n;
+        const int kk = kept;
         for (int i = threadIdx.x; i < kk; i += blockDim.x) {
             const uint64_t key = s_key[i];
             int a = i, b = i + 1;
@@ -248,6 +318,10 @@ int sg_topn_select_rows(int64_t n_cand, const int32_t *cand_row, const int32_t *
     int dev = 0, n_sm = 0;
     SG_CUDA_TRY(cudaGetDevice(&dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    sel_rows_mid_kernel<<<(unsigned)(n_sm * 2), SEL_MID_WARPS * 32, 0, st>>>(row_begin, row_start, b_col, b_score, top_n,
+                                                                            out_indptr, out_row, out_col, out_score,
+                                                                            big_rows, n_big);
+    SG_LAUNCH_CHECK();
     sel_rows_big_kernel<<<(unsigned)(n_sm * 2), 256, 0, st>>>(row_begin, row_start, b_col, b_score, top_n, out_indptr,
                                                              out_row, out_col, out_score, big_rows, n_big);
     SG_LAUNCH_CHECK();

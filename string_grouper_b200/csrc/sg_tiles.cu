@@ -38,9 +38,11 @@ struct __align__(16) TileDesc {
     int n_dist;             // distinct features of the tile = buckets
 };
 
+constexpr int TL_LONG = 64;          // buckets from this length on are streamed by the whole warp
 constexpr int TL_W = 256;            // columns per tile (accumulator: 256 x u32 = 1 KB per warp)
 constexpr int TL_CBUF = 96;          // candidate buffer entries per warp
 constexpr float TL_FIX = 32768.f;    // weights in 2^-15 units, products in 2^-30 units
+constexpr int TL_WARP_BYTES = TL_W * 4 + 64 * 4 + 32 * 8 + TL_CBUF * 8;
 constexpr int TL_HEAD_BYTES = 128;   // mbarrier, item broadcast, survivor count
 
 __host__ __device__ __forceinline__ int a16(int x) { return (x + 15) & ~15; }
@@ -260,75 +262,59 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
                    const uint32_t *__restrict__ maxw_h, int Tp, int64_t T, const float *__restrict__ tile_bound,
                    uint32_t *__restrict__ mask, int64_t mask_stride) {
     __shared__ uint32_t buf[FL_WORDS][FL_RANKS + 1];
-    constexpr int RPW = FL_RANKS / FL_WARPS;          // ranks per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rank0 = (int64_t)blockIdx.x * FL_RANKS;
     const int n_words = Tp >> 5;
     const int half_tp = Tp >> 1;
-    // the warp's ranks: kept features in registers (one per lane)
-    int nf[RPW], f0[RPW];
-    float thr_r[RPW], xp[RPW], slack[RPW];
-    __half2 a2[RPW];
-#pragma unroll
-    for (int ri = 0; ri < RPW; ++ri) {
-        const int64_t r = rank0 + warp * RPW + ri;
-        nf[ri] = 0; f0[ri] = 0; thr_r[ri] = 0.f; xp[ri] = 0.f;
-        a2[ri] = __float2half2_rn(0.f);
-        if (r < n_ranks) {
-            const int4 info = rowinfo[r];
-            nf[ri] = info.y;
-            thr_r[ri] = __int_as_float(info.z);
-            xp[ri] = __int_as_float(info.w);
-            if (lane < info.y) {
-                const int2 fa = lpack[(int64_t)info.x + lane];
-                f0[ri] = fa.x;
-                // rounded up: the bound must not fall short
-                a2[ri] = __half2half2(__float2half_ru((float)fa.y * (1.f / TL_FIX)));
-            }
-        }
-        const int nk = nf[ri] < 32 ? nf[ri] : 32;
-        slack[ri] = 5e-4f * (float)nk + 1e-4f;        // fp16 arithmetic of the bound
-    }
     for (int w0 = 0; w0 < n_words; w0 += FL_WORDS) {
         const int w1 = w0 + FL_WORDS < n_words ? w0 + FL_WORDS : n_words;
-        // batches outermost: the 32 neighbouring ranks of the CTA (similar rows: mostly the same features) read the same
-        // block-maxima lines within a short time, so most of these loads hit L1 instead of L2
-        for (int wd = w0; wd < w1; wd += 2) {
-            const int tb = wd << 5;                       // first tile of the batch
-            const int t0 = tb + 2 * lane;
-            const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
-            const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
-#pragma unroll
-            for (int ri = 0; ri < RPW; ++ri) {
+        for (int ri = 0; ri < FL_RANKS / FL_WARPS; ++ri) {
+            const int rr = warp * (FL_RANKS / FL_WARPS) + ri;
+            const int64_t r = rank0 + rr;
+            int nf = 0;
+            float thr_r = 0.f, xp = 0.f;
+            int f0 = 0;
+            __half2 a2 = __float2half2_rn(0.f);
+            if (r < n_ranks) {
+                const int4 info = rowinfo[r];
+                nf = info.y;
+                thr_r = __int_as_float(info.z);
+                xp = __int_as_float(info.w);
+                if (lane < nf) {
+                    const int2 fa = lpack[(int64_t)info.x + lane];
+                    f0 = fa.x;
+                    // rounded up: the bound must not fall short
+                    a2 = __half2half2(__float2half_ru((float)fa.y * (1.f / TL_FIX)));
+                }
+            }
+            const int nk = nf < 32 ? nf : 32;
+            const float slack = 5e-4f * (float)nk + 1e-4f;    // fp16 arithmetic of the bound
+            for (int wd = w0; wd < w1; wd += 2) {
+                const int tb = wd << 5;                       // first tile of the batch
                 unsigned m_even = 0, m_odd = 0;
-                if (nf[ri] > 32) {                        // more kept features than lanes: every tile is walked
+                const int t0 = tb + 2 * lane;
+                if (nf > 32) {                                // more kept features than lanes: every tile is walked
                     m_even = __ballot_sync(FULL, t0 < T);
                     m_odd = __ballot_sync(FULL, t0 + 1 < T);
-                } else if (nf[ri] > 0) {
-                    const int nk = nf[ri];
+                } else if (nf > 0) {
                     __half2 ub2 = __float2half2_rn(0.f);
-                    for (int k0 = 0; k0 < nk; k0 += 8) {      // eight loads in flight per lane
-                        uint32_t m[8];
-                        __half2 ak[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int kk = k0 + j;
-                            const int fk = __shfl_sync(FULL, f0[ri], kk & 31);
-                            ak[j] = __shfl_sync(FULL, a2[ri], kk & 31);
-                            m[j] = kk < nk ? mrow[(int64_t)fk * half_tp] : 0u;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ub2 = __hfma2(ak[j], *reinterpret_cast<const __half2 *>(&m[j]), ub2);
+                    const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
+                    for (int k = 0; k < nk; ++k) {
+                        const int fk = __shfl_sync(FULL, f0, k);
+                        const __half2 ak2 = __shfl_sync(FULL, a2, k);
+                        const uint32_t m = mrow[(int64_t)fk * half_tp];
+                        ub2 = __hfma2(ak2, *reinterpret_cast<const __half2 *>(&m), ub2);
                     }
                     const float2 ub = __half22float2(ub2);
-                    const float thr0 = xp[ri] > 0.f ? fmaxf(fmaf(-xp[ri], tb2.x, thr_r[ri]), 0.f) : thr_r[ri];
-                    const float thr1 = xp[ri] > 0.f ? fmaxf(fmaf(-xp[ri], tb2.y, thr_r[ri]), 0.f) : thr_r[ri];
-                    m_even = __ballot_sync(FULL, t0 < T && ub.x + slack[ri] > thr0);
-                    m_odd = __ballot_sync(FULL, t0 + 1 < T && ub.y + slack[ri] > thr1);
+                    const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];
+                    const float thr0 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.x, thr_r), 0.f) : thr_r;
+                    const float thr1 = xp > 0.f ? fmaxf(fmaf(-xp, tb2.y, thr_r), 0.f) : thr_r;
+                    m_even = __ballot_sync(FULL, t0 < T && ub.x + slack > thr0);
+                    m_odd = __ballot_sync(FULL, t0 + 1 < T && ub.y + slack > thr1);
                 }
                 if (lane == 0) {
-                    buf[wd - w0][warp * RPW + ri] = m_even;
-                    buf[wd - w0 + 1][warp * RPW + ri] = m_odd;
+                    buf[wd - w0][rr] = m_even;
+                    buf[wd - w0 + 1][rr] = m_odd;
                 }
             }
         }
@@ -342,73 +328,151 @@ tile_filter_kernel(int64_t n_ranks, const int4 *__restrict__ rowinfo, const int2
 // ---------------------------------------------------------------------------
 // candidates
 // ---------------------------------------------------------------------------
-// shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loop)
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint32_t v;
-    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void sts128z(uint32_t a) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-// old = (pred ? atomicAdd(shared a, v) : 0), without a branch
-__device__ __forceinline__ uint32_t atoms_add_if(uint32_t a, uint32_t v, bool pred) {
-    uint32_t old;
-    asm volatile(
-        "{ .reg .pred p; setp.ne.u32 p, %3, 0; mov.u32 %0, 0; @p atom.shared.add.u32 %0, [%1], %2; }"
-        : "=r"(old)
-        : "r"(a), "r"(v), "r"((unsigned)pred)
-        : "memory");
-    return old;
-}
-__device__ __forceinline__ uint32_t lds32_if(uint32_t a, bool pred) {
-    uint32_t v;
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; mov.u32 %0, 0; @p ld.shared.u32 %0, [%1]; }"
-                 : "=r"(v)
-                 : "r"(a), "r"((unsigned)pred));
-    return v;
+constexpr int tl_min_ctas(int nw) { return nw == 16 ? 1 : 3; }
+
+struct WarpCtx {
+    uint32_t *acc;          // TL_W partial scores, 2^-30 units
+    uint32_t *flags;        // bucket-start bits of the concatenated list
+    int2 *dk;               // per non-empty short bucket: {posting index - start in the list, left weight}
+    int2 *cbuf;             // buffered candidates {left rank, column position}
+    int ccount;
+};
+
+__device__ __forceinline__ void flush_candidates(WarpCtx &cx, int lane, const int32_t *__restrict__ perm_a,
+                                                 int64_t row_begin, const int32_t *__restrict__ perm_b,
+                                                 int32_t *__restrict__ cand_row, int32_t *__restrict__ cand_col,
+                                                 unsigned long long cap, unsigned long long *cand_count) {
+    __syncwarp();
+    if (cx.ccount > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)cx.ccount);
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < cx.ccount; i += 32) {
+            const int2 c = cx.cbuf[i];
+            if (base + i < cap) {
+                cand_row[base + i] = (int32_t)(perm_a ? perm_a[c.x] : row_begin + c.x);
+                cand_col[base + i] = perm_b ? perm_b[c.y] : c.y;
+            }
+        }
+        cx.ccount = 0;
+    }
+    __syncwarp();
 }
 
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
-    asm volatile("{ .reg .u16 h; cvt.u16.u32 h, %1; st.shared.u16 [%0], h; }" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// the shared-window base as a value the compiler cannot re-derive (it would recompute it from the CTA id per use)
-__device__ __forceinline__ uint32_t opaque(uint32_t x) {
-    asm volatile("mov.u32 %0, %0;" : "+r"(x));
-    return x;
-}
+// report the columns whose partial score crossed the threshold in this step
+#define TL_EMIT(crossed_, colbyte_)                                                                       \
+    do {                                                                                                  \
+        const unsigned em_ = __ballot_sync(FULL, (crossed_));                                             \
+        if (em_) {                                                                                        \
+            if ((crossed_)) cx.cbuf[cx.ccount + __popc(em_ & lt_mask)] = make_int2(rank_id, col0 + ((int)(colbyte_) >> 2)); \
+            cx.ccount += __popc(em_);                                                                     \
+            if (cx.ccount > TL_CBUF - 32)                                                                 \
+                flush_candidates(cx, lane, perm_a, row_begin, perm_b, cand_row, cand_col, cap, cand_count);   \
+        }                                                                                                 \
+    } while (0)
 
-// Thread-per-pair layout.  A (left row, tile) pair is tiny — about 13 kept features, 70 postings, 2 columns over the
-// threshold — so warp-collective processing (prefix sums, owner search, votes per 32 postings) costs more than the work.
-// Here every LANE owns one pair: its 256 partial scores are 16-bit fixed point (2^-15 units) in a lane-private column
-// of the warp's accumulator block (acc[col][lane]: conflict-free, no atomics), its features arrive by cp.async into a
-// lane-private row of a staging block, its buckets are found and walked serially.  32 pairs advance per warp step.
-constexpr int TP_FS = 16;                           // features staged per pair and round (rows with more: more rounds)
-constexpr int TP_FSTRIDE = TP_FS + 1;               // 8-byte entries per pair row, padded: lane = pair access is conflict-free
-constexpr int TP_ACC_BYTES = TL_W * 32 * 2;         // 16 KB: 256 columns x 32 pairs x u16
-constexpr int TL_WARP_BYTES2 = TP_ACC_BYTES + 32 * TP_FSTRIDE * 8 + TL_CBUF * 8;
-constexpr int tl_min_ctas(int) { return 1; }
-__host__ __device__ constexpr int tl_list(int nw) { return nw * 256 + nw * 32; }     // survivor ranks held per round
-constexpr float TP_FIX = 32768.f;
+// One (left row, tile) pair: buckets of the row's kept features through the bitmap directory, long buckets streamed
+// by the warp, all others walked as one concatenated list; columns whose partial score crosses the threshold are
+// buffered as candidates.
+#define TL_PAIR(rank_id_, info_, fa_first_)                                                                         \
+    do {                                                                                                            \
+        const int rank_id = (rank_id_);                                                                             \
+        const int cur_p0 = (info_).x, cur_nf = (info_).y;                                                           \
+        const float thr_r = __int_as_float((info_).z);                                                              \
+        const float xp = __int_as_float((info_).w);                                                                 \
+        const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;                                \
+        const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 3.9f) * (TL_FIX * TL_FIX));                   \
+        bool touched = false;                                                                                       \
+        ++n_pairs;                                                                                                  \
+        for (int fb = 0; fb < cur_nf; fb += 32) {                                                                   \
+            int2 e_fa = (fa_first_);                                                                                \
+            if (fb > 0) {                                                                                           \
+                e_fa = make_int2(0, 0);                                                                             \
+                if (fb + lane < cur_nf) e_fa = lpack[(int64_t)cur_p0 + fb + lane];                                  \
+            }                                                                                                       \
+            int len = 0, o0 = 0;                                                                                    \
+            if (fb + lane < cur_nf) {                                                                               \
+                const unsigned f = (unsigned)e_fa.x;                                                                \
+                const uint32_t bmw = bitmap[f >> 5];                                                                \
+                if ((bmw >> (f & 31)) & 1u) {                                                                       \
+                    const int jb = (int)prefix[f >> 5] + __popc(bmw & ((1u << (f & 31)) - 1u));                     \
+                    o0 = off[jb];                                                                                   \
+                    len = (int)off[jb + 1] - o0;                                                                    \
+                }                                                                                                   \
+            }                                                                                                       \
+            const unsigned aq = (unsigned)e_fa.y;                                                                   \
+            unsigned lm = __ballot_sync(FULL, len >= TL_LONG);                                                      \
+            while (lm) {                                                                                            \
+                const int s_ = __ffs(lm) - 1;                                                                       \
+                lm &= lm - 1;                                                                                       \
+                const int b0 = __shfl_sync(FULL, o0, s_);                                                           \
+                const int b1 = b0 + __shfl_sync(FULL, len, s_);                                                     \
+                const unsigned ak = __shfl_sync(FULL, aq, s_);                                                      \
+                n_walked += (unsigned)(b1 - b0);                                                                    \
+                for (int p = b0; p < b1; p += 32) {                                                                 \
+                    bool crossed = false;                                                                           \
+                    unsigned cb = 0;                                                                                \
+                    if (p + lane < b1) {                                                                            \
+                        const uint32_t e = post[p + lane];                                                          \
+                        const unsigned x = (e >> 16) * ak;                                                          \
+                        cb = e & 0xffffu;                                                                           \
+                        const unsigned old = atomicAdd(                                                             \
+                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
+                        crossed = old <= thr_c && old + x > thr_c;                                                  \
+                    }                                                                                               \
+                    TL_EMIT(crossed, cb);                                                                           \
+                }                                                                                                   \
+                touched = true;                                                                                     \
+            }                                                                                                       \
+            const int ln = len >= TL_LONG ? 0 : len;                                                                \
+            int incl = ln;                                                                                          \
+            _Pragma("unroll") for (int o = 1; o < 32; o <<= 1) {                                                    \
+                const int up = __shfl_up_sync(FULL, incl, o);                                                       \
+                if (lane >= o) incl += up;                                                                          \
+            }                                                                                                       \
+            const int total = __shfl_sync(FULL, incl, 31);                                                          \
+            if (total > 0) {                                                                                        \
+                touched = true;                                                                                     \
+                n_walked += (unsigned)total;                                                                        \
+                const unsigned nz = __ballot_sync(FULL, ln > 0);                                                    \
+                if (ln > 0) {                                                                                       \
+                    const int st = incl - ln;                                                                       \
+                    cx.dk[__popc(nz & lt_mask)] = make_int2(o0 - st, (int)aq);                                      \
+                    atomicOr(&cx.flags[st >> 5], 1u << (st & 31));                                                  \
+                }                                                                                                   \
+                __syncwarp();                                                                                       \
+                int kbase = -1;                                                                                     \
+                for (int s0 = 0; s0 < total; s0 += 32) {                                                            \
+                    const uint32_t fw = cx.flags[s0 >> 5];                                                          \
+                    const int k = kbase + __popc(fw & le_mask);                                                     \
+                    kbase += __popc(fw);                                                                            \
+                    __syncwarp();                                                                                   \
+                    if (lane == 0) cx.flags[s0 >> 5] = 0u;                                                          \
+                    bool crossed = false;                                                                           \
+                    unsigned cb = 0;                                                                                \
+                    if (s0 + lane < total) {                                                                        \
+                        const int2 dd = cx.dk[k];                                                                   \
+                        const uint32_t e = post[dd.x + s0 + lane];                                                  \
+                        const unsigned x = (e >> 16) * (unsigned)dd.y;                                              \
+                        cb = e & 0xffffu;                                                                           \
+                        const unsigned old = atomicAdd(                                                             \
+                            reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(cx.acc) + cb), x);       \
+                        crossed = old <= thr_c && old + x > thr_c;                                                  \
+                    }                                                                                               \
+                    TL_EMIT(crossed, cb);                                                                           \
+                }                                                                                                   \
+                __syncwarp();                                                                                       \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (touched) {                                                                                              \
+            __syncwarp();                                                                                           \
+            _Pragma("unroll") for (int c = 0; c < TL_W * 4 / 16 / 32; ++c)                                          \
+                reinterpret_cast<uint4 *>(cx.acc)[c * 32 + lane] = zero4;                                           \
+            __syncwarp();                                                                                           \
+        }                                                                                                           \
+    } while (0)
+
+__host__ __device__ constexpr int tl_list(int nw) { return nw * 256; }     // survivor ranks per scan round (every warp scans 256 ranks)
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, tl_min_ctas(NW))
@@ -428,15 +492,16 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
     uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + TL_HEAD_BYTES);
     unsigned char *stage = smem + TL_HEAD_BYTES + tl_list(NW) * 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t smem_s = opaque(smem_u32(smem));
-    const uint32_t stage_s = smem_s + TL_HEAD_BYTES + tl_list(NW) * 4;
-    const uint32_t warp_s = stage_s + stage_bytes + warp * TL_WARP_BYTES2;
-    const uint32_t acc_s = warp_s + lane * 2;                               // this lane's column of partial scores
-    const uint32_t feat_s = warp_s + TP_ACC_BYTES + lane * (TP_FSTRIDE * 8);  // this lane's feature / bucket row
-    const uint32_t cbuf_s = warp_s + TP_ACC_BYTES + 32 * TP_FSTRIDE * 8;
-    int ccount = 0;
-    for (int c = lane; c < TP_ACC_BYTES / 16; c += 32) sts128z(warp_s + c * 16);
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    unsigned char *wa = stage + stage_bytes + (size_t)warp * TL_WARP_BYTES;
+    WarpCtx cx;
+    cx.acc = reinterpret_cast<uint32_t *>(wa);
+    cx.flags = reinterpret_cast<uint32_t *>(wa + TL_W * 4);
+    cx.dk = reinterpret_cast<int2 *>(wa + TL_W * 4 + 64 * 4);
+    cx.cbuf = reinterpret_cast<int2 *>(wa + TL_W * 4 + 64 * 4 + 32 * 8);
+    cx.ccount = 0;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int c = lane; c < (TL_W * 4 + 64 * 4) / 16; c += 32) reinterpret_cast<uint4 *>(wa)[c] = zero4;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         *s_count = 0;
@@ -445,27 +510,7 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
 
     const unsigned long long n_items = (unsigned long long)T * (unsigned long long)n_seg;
     unsigned parity = 0;
-    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added by this lane
-
-    // buffered candidates -> global list (one atomic per flush)
-    auto flush = [&]() {
-        __syncwarp();
-        if (ccount > 0) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)ccount);
-            base = __shfl_sync(FULL, base, 0);
-            for (int i = lane; i < ccount; i += 32) {
-                const uint2 c = lds64(cbuf_s + i * 8);
-                if (base + i < cap) {
-                    cand_row[base + i] = (int32_t)(perm_a ? perm_a[c.x] : row_begin + c.x);
-                    cand_col[base + i] = perm_b ? perm_b[c.y] : (int32_t)c.y;
-                }
-            }
-            ccount = 0;
-        }
-        __syncwarp();
-    };
-
+    unsigned long long n_pairs = 0, n_walked = 0;       // (row, tile) pairs taken / postings added by this warp
     for (;;) {
         // ---- next (tile, rank segment); its blob goes into shared memory by bulk copies (TMA)
         if (threadIdx.x == 0) {
@@ -487,10 +532,11 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         const int t = (int)(it / (unsigned long long)n_seg);
         const int64_t seg = (int64_t)(it % (unsigned long long)n_seg);
         const TileDesc d = tdesc[t];
-        const uint32_t post_s = stage_s;
-        const uint32_t bitmap_s = stage_s + a16(4 * d.n_post);
-        const uint32_t prefix_s = bitmap_s + 4 * bw;
-        const uint32_t off_s = prefix_s + a16(2 * bw);
+        const uint32_t *post = reinterpret_cast<const uint32_t *>(stage);
+        const uint32_t *bitmap = reinterpret_cast<const uint32_t *>(stage + a16(4 * d.n_post));
+        const unsigned short *prefix = reinterpret_cast<const unsigned short *>(stage + a16(4 * d.n_post) + 4 * bw);
+        const unsigned short *off =
+            reinterpret_cast<const unsigned short *>(stage + a16(4 * d.n_post) + 4 * bw + a16(2 * bw));
         const float tbound = tile_bound[t];
         const int col0 = t * TL_W;
         const int64_t rank_lo = seg * seg_ranks;
@@ -499,150 +545,77 @@ tile_candidates_kernel(const int32_t *__restrict__ perm_a, int64_t n_ranks, int6
         const int bit = (t & 63) >> 1;
         bool staged = false;
 
-        int64_t base = rank_lo;
-        while (base < rank_hi) {
-            // ---- scan rounds: every warp tests 256 ranks per round (eight coalesced mask words in flight) and appends
-            // the survivors to the CTA's list, until the list holds a full 32-pair chunk for every warp
-            int count = 0;
-            for (;;) {
-                const int64_t gbase = base + ((int64_t)warp << 8);
-                uint32_t wsv[8];
+        for (int64_t base = rank_lo; base < rank_hi; base += (int64_t)NW * 256) {
+            // ---- scan round: every warp tests 256 ranks (eight coalesced mask words in flight) and appends the
+            // survivors to the CTA's list.  Survivors cluster in rank order (similar rows are neighbours), so the list
+            // is dealt out to the warps round-robin afterwards.
+            const int64_t gbase = base + ((int64_t)warp << 8);
+            uint32_t wsv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int64_t r = gbase + j * 32 + lane;
-                    wsv[j] = r < rank_hi ? mrow[r] : 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
-                    if (sv) {
-                        int pos = 0;
-                        if (lane == 0) pos = atomicAdd(s_count, __popc(sv));
-                        pos = __shfl_sync(FULL, pos, 0);
-                        if ((sv >> lane) & 1u) s_list[pos + __popc(sv & lt_mask)] = (uint32_t)(gbase + j * 32 + lane);
-                    }
-                }
-                base += (int64_t)NW * 256;
-                __syncthreads();
-                count = *reinterpret_cast<volatile int *>(s_count);
-                if (count >= NW * 32 || base >= rank_hi) break;
-                __syncthreads();          // everybody has read the count before the next round appends
+            for (int j = 0; j < 8; ++j) {
+                const int64_t r = gbase + j * 32 + lane;
+                wsv[j] = r < rank_hi ? mrow[r] : 0u;
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned sv = __ballot_sync(FULL, (wsv[j] >> bit) & 1u);
+                if (sv) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(s_count, __popc(sv));
+                    pos = __shfl_sync(FULL, pos, 0);
+                    if ((sv >> lane) & 1u) s_list[pos + __popc(sv & lt_mask)] = (uint32_t)(gbase + j * 32 + lane);
+                }
+            }
+            __syncthreads();
+            const int count = *reinterpret_cast<volatile int *>(s_count);
             if (count > 0) {
                 if (!staged) {
                     mbar_wait(mbar, parity);
                     staged = true;
                 }
-                // ---- chunks of 32 consecutive list entries (neighbouring ranks: similar rows, similar work), dealt
-                // round-robin to the warps; lane = pair
-                for (int c0 = warp * 32; c0 < count; c0 += NW * 32) {
-                    const int idx = c0 + lane;
-                    int r = 0;
-                    int4 info = make_int4(0, 0, 0, 0);
-                    if (idx < count) {
-                        r = (int)s_list[idx];
-                        info = rowinfo[r];
+                // ---- this warp's pairs: list entries warp, warp + NW, ...; row record two ahead, features one ahead
+                int i = warp;
+                int r_c = 0, r_n = 0;
+                int4 info_c = make_int4(0, 0, 0, 0), info_n = info_c;
+                int2 fa_c = make_int2(0, 0);
+                if (i < count) {
+                    r_c = (int)s_list[i];
+                    info_c = rowinfo[r_c];
+                }
+                if (i + NW < count) {
+                    r_n = (int)s_list[i + NW];
+                    info_n = rowinfo[r_n];
+                }
+                if (i < count && lane < info_c.y) fa_c = lpack[(int64_t)info_c.x + lane];
+                while (i < count) {
+                    int2 fa_n = make_int2(0, 0);
+                    if (i + NW < count && lane < info_n.y) fa_n = lpack[(int64_t)info_n.x + lane];
+                    int r_nn = 0;
+                    int4 info_nn = make_int4(0, 0, 0, 0);
+                    if (i + 2 * NW < count) {
+                        r_nn = (int)s_list[i + 2 * NW];
+                        info_nn = rowinfo[r_nn];
                     }
-                    const int nf = info.y;                      // 0: no pair in this lane
-                    const float thr_r = __int_as_float(info.z);
-                    const float xp = __int_as_float(info.w);
-                    const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tbound, thr_r), 0.f) : thr_r;
-                    const unsigned thr_c = (unsigned)__float2uint_rd(fminf(thr_f, 1.99f) * TP_FIX);
-                    if (nf > 0) ++n_pairs;
-                    for (int fb0 = 0; __any_sync(FULL, fb0 < nf); fb0 += TP_FS) {
-                        // features [fb0, fb0 + TP_FS) of every pair -> the pair's staging row (cp.async: 32 rows in
-                        // flight, no registers); two pairs per step, 16 lanes each
-                        for (int jj = 0; jj < 32; jj += 2) {
-                            const int j = jj + (lane >> 4), k = lane & 15;
-                            const int p0j = __shfl_sync(FULL, info.x, j);
-                            const int nfj = __shfl_sync(FULL, nf, j);
-                            if (fb0 + k < nfj)
-                                cp_async8(warp_s + TP_ACC_BYTES + (j * TP_FSTRIDE + k) * 8, lpack + (int64_t)p0j + fb0 + k);
-                        }
-                        cp_async_wait_all();
-                        __syncwarp();
-                        // buckets of this lane's features through the bitmap directory, compacted in place
-                        const int myn = nf - fb0 < TP_FS ? nf - fb0 : TP_FS;
-                        int nb = 0;
-                        for (int k = 0; __any_sync(FULL, k < myn); ++k) {
-                            if (k < myn) {
-                                const uint2 fa = lds64(feat_s + k * 8);
-                                const unsigned f = fa.x;
-                                const uint32_t bmw = lds32(bitmap_s + ((f >> 5) << 2));
-                                if ((bmw >> (f & 31)) & 1u) {
-                                    const uint32_t jb = lds16(prefix_s + ((f >> 5) << 1)) + __popc(bmw & ((1u << (f & 31)) - 1u));
-                                    const uint32_t o0 = lds16(off_s + (jb << 1));
-                                    const uint32_t o1 = lds16(off_s + (jb << 1) + 2);
-                                    sts64(feat_s + nb * 8, o0 | ((o1 - o0) << 16), fa.y);
-                                    ++nb;
-                                }
-                            }
-                        }
-                        // walk: one posting per lane and step; products a_q * w_q >> 15 into the lane's own column
-                        int bi = 0;
-                        uint32_t p = 0, pend = 0, aq = 0;
-                        bool done = nb == 0;
-                        for (;;) {
-                            if (!done && p == pend) {
-                                if (bi < nb) {
-                                    const uint2 b = lds64(feat_s + bi * 8);
-                                    ++bi;
-                                    p = b.x & 0xffffu;
-                                    pend = p + (b.x >> 16);
-                                    aq = b.y;
-                                    n_walked += (b.x >> 16);
-                                } else {
-                                    done = true;
-                                }
-                            }
-                            if (__all_sync(FULL, done)) break;
-                            bool crossed = false;
-                            uint32_t cb = 0;
-                            if (!done) {
-                                const uint32_t e = lds32(post_s + (p << 2));
-                                ++p;
-                                const uint32_t x = ((e >> 16) * aq) >> 15;
-                                cb = e & 0xffffu;                              // column * 4
-                                const uint32_t a_addr = acc_s + (cb << 4);     // column * 64 bytes + lane * 2
-                                const uint32_t old = lds16(a_addr);
-                                const uint32_t now = old + x;
-                                sts16(a_addr, now);
-                                crossed = old <= thr_c && now > thr_c;
-                            }
-                            const unsigned em = __ballot_sync(FULL, crossed);
-                            if (em) {
-                                if (crossed) sts64(cbuf_s + (ccount + __popc(em & lt_mask)) * 8, (uint32_t)r, (uint32_t)(col0 + (int)(cb >> 2)));
-                                ccount += __popc(em);
-                                if (ccount > TL_CBUF - 32) flush();
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    // clear the warp's accumulator block (contiguous 16 KB)
-#pragma unroll 4
-                    for (int c = 0; c < TP_ACC_BYTES / 16 / 32; ++c) sts128z(warp_s + (c * 32 + lane) * 16);
-                    __syncwarp();
+                    TL_PAIR(r_c, info_c, fa_c);
+                    r_c = r_n; info_c = info_n; fa_c = fa_n;
+                    r_n = r_nn; info_n = info_nn;
+                    i += NW;
                 }
             }
             __syncthreads();
             if (threadIdx.x == 0) *s_count = 0;
+            // (the next round's appends come after the next __syncthreads-separated scan loads; the reset is ordered
+            // before them by the barrier below)
             __syncthreads();
         }
         if (!staged) mbar_wait(mbar, parity);     // nothing survived: still consume the phase before the stage is reused
         parity ^= 1u;
         __syncthreads();      // every warp is done with the staged tile before the next one is copied over it
     }
-    flush();
-    if (walk_stats) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
-            n_walked += __shfl_xor_sync(FULL, n_walked, o);
-        }
-        if (lane == 0) {
-            atomicAdd(walk_stats, n_pairs);
-            atomicAdd(walk_stats + 1, n_walked);
-        }
+    flush_candidates(cx, lane, perm_a, row_begin, perm_b, cand_row, cand_col, cap, cand_count);
+    if (walk_stats && lane == 0) {
+        atomicAdd(walk_stats, n_pairs);
+        atomicAdd(walk_stats + 1, n_walked);
     }
 }
 
@@ -773,7 +746,7 @@ int sg_tiles_filter(int64_t n_ranks, const void *rowinfo, const void *lpack, con
 }
 
 size_t sg_tiles_smem_bytes(int stage_bytes, int warps_per_cta) {
-    return (size_t)TL_HEAD_BYTES + (size_t)tl_list(warps_per_cta) * 4 + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES2;
+    return (size_t)TL_HEAD_BYTES + (size_t)tl_list(warps_per_cta) * 4 + (size_t)a16(stage_bytes) + (size_t)warps_per_cta * TL_WARP_BYTES;
 }
 
 int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begin, const void *rowinfo,
@@ -784,8 +757,7 @@ int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begi
                         unsigned long long *walk_stats, int warps_per_cta, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_ranks <= 0 || n_right <= 0) return SG_OK;
-    if (warps_per_cta != 4 && warps_per_cta != 6 && warps_per_cta != 8)
-        return fail(SG_ERR_INVALID, "warps_per_cta must be 4, 6 or 8");
+    if (warps_per_cta != 8 && warps_per_cta != 16) return fail(SG_ERR_INVALID, "warps_per_cta must be 8 or 16");
     int dev = 0, n_sm = 0, smem_optin = 0;
     SG_CUDA_TRY(cudaGetDevice(&dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -818,7 +790,7 @@ int sg_tiles_candidates(const int32_t *perm_a, int64_t n_ranks, int64_t row_begi
             (const TileDesc *)tile_desc, (const unsigned char *)blob, T, bw, tile_bound, perm_b, seg_ranks, n_seg,   \
             cand_row, cand_col, (unsigned long long)cand_cap, cand_count, queue, walk_stats, stage_bytes);           \
     } while (0)
-    if (warps_per_cta == 4) SG_TL_LAUNCH(4); else if (warps_per_cta == 6) SG_TL_LAUNCH(6); else SG_TL_LAUNCH(8);
+    if (warps_per_cta == 16) SG_TL_LAUNCH(16); else SG_TL_LAUNCH(8);
 #undef SG_TL_LAUNCH
     SG_LAUNCH_CHECK();
     return SG_OK;

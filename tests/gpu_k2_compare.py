@@ -24,9 +24,9 @@ for kernel in (["tiles", "row"] if which == "both" else [which]):
         got = D.cossim_topn(A, A, 20, 0.8, stats=st, kernel=kernel)
         torch.cuda.synchronize(); tk = time.time() - t
         kms = sum(a.elapsed_time(b) for a, b in st["candidate_events"])
-        print("%s rep %d: cossim_topn %.1f ms, candidates launch(es) %.2f ms, cand=%d above=%d nnz=%d pairs=%s postings=%s stage=%s prune=%s" % (
+        print("%s rep %d: cossim_topn %.1f ms, candidates launch(es) %.2f ms, cand=%d above=%d nnz=%d pairs=%s postings=%s stage=%s prune=%s select=%s" % (
             kernel, rep, tk * 1e3, kms, st["n_candidates"], st["n_above_threshold"], got.nnz, st.get("pairs_walked"),
-            st.get("postings_walked"), st.get("stage_bytes"), st.get("prune")), flush=True)
+            st.get("postings_walked"), st.get("stage_bytes"), st.get("prune"), st.get("select")), flush=True)
     res[kernel] = got.host_triples()
 if len(res) == 2:
     a, b = res["tiles"], res["row"]

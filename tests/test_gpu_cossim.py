@@ -39,7 +39,7 @@ def test_self_match_matches_oracle(n, top_n, thr, dtype, kernel):
     names = make_names(n, seed=1)
     st = {}
     m, d, ref, got = _run(names, None, top_n, thr, dtype, kernel=kernel, stats=st)
-    assert st["kernel"] == kernel          # the TMA-staged tile kernel is the default path for K1 output
+    assert st["kernel"] == kernel          # both K2 formulations against the oracle
     if kernel == "tiles":
         assert st["postings_walked"] > 0 and st["pairs_walked"] > 0
     gr, gc, gs = got.host_triples()
@@ -167,7 +167,9 @@ def test_row_selection_paths_agree(monkeypatch):
             for top_n in (20, 1, 3000):
                 got = D.cossim_topn(A, A, top_n, 0.8, stats=st)
                 out[(mode, top_n)] = got.host_triples() + (got.max_row,)
-            assert st["select"] == ("sort" if (mode == "sort" or big > 4096) else "rows")
+                # rows longer than one CTA's shared memory are ranked in pieces as long as top_n <= cap / 2
+                want = "sort" if (mode == "sort" or (big > 4096 and top_n > 2048)) else "rows"
+                assert st["select"] == want, (big, top_n, st["select"])
         for top_n in (20, 1, 3000):
             a, b = out[("rows", top_n)], out[("sort", top_n)]
             assert a[3] == b[3]
