@@ -682,7 +682,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     out_score = _empty(n_cand, t.float64, dev)
     tail = t.zeros(2, dtype=t.int64, device=dev)            # [0] out_nnz, [1] max_row (int32 view)
     rows_cap = int(L.sg_topn_rows_cap())
-    if (max_row_cnt <= rows_cap or top_n <= rows_cap // 2) and SELECT_MODE != "sort":
+    if (top_n <= 32 or max_row_cnt <= rows_cap or top_n <= rows_cap // 2) and SELECT_MODE != "sort":
         # survivors bucketed by row, every row ranked on its own (warp shuffle network / one CTA in shared memory)
         ws_bytes = int(L.sg_topn_select_rows_workspace_bytes(n_cand, n_rows))
         ws = _empty(ws_bytes, t.uint8, dev)

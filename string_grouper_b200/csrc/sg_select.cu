@@ -4,9 +4,11 @@
 // A.3): per left row keep the `top_n` largest scores strictly above the threshold, emit them value-descending
 // (sort=True).  sg_topn_select (sg_cossim.cu) does this with three global radix sorts over all survivors; here the
 // survivors are bucketed by row (the exact re-score has already counted them per row), and every row is ranked on
-// its own: rows of up to 32 survivors (nearly all) by one warp with a shuffle bitonic network, rows of up to 512 by
-// one warp in shared memory, longer rows by one CTA (in pieces of SEL_BIG_CAP with the best top_n carried along, which
-// needs top_n <= SEL_BIG_CAP / 2; otherwise the caller uses sg_topn_select).
+// its own.  top_n <= 32 (max_n_matches defaults to 20): one warp per row streams the row 32 survivors at a time and
+// keeps the best 32 in registers (shuffle bitonic sort + merge), whatever the row length.  Larger top_n: rows of up to
+// 32 survivors by the warp network, up to 512 by one warp in shared memory, longer rows by one CTA (in pieces of
+// SEL_BIG_CAP with the best top_n carried along, which needs top_n <= SEL_BIG_CAP / 2; otherwise the caller uses
+// sg_topn_select).
 //
 // Order: score descending; among EQUAL scores the larger column wins the cut (what the upstream traversal keeps for
 // identical strings) and the survivors of a tie are written in ascending column order — the rule of sg_topn_select.
@@ -54,32 +56,8 @@ __device__ __forceinline__ bool sel_before(uint64_t ka, int32_t ca, uint64_t kb,
     return ka < kb || (ka == kb && ca > cb);
 }
 
-// one warp per row; rows with more than 32 survivors are appended to `big_rows`
-__global__ void __launch_bounds__(256)
-sel_rows_small_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restrict__ row_start,
-                      const int32_t *__restrict__ b_col, const double *__restrict__ b_score, int top_n,
-                      const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_row,
-                      int32_t *__restrict__ out_col, double *__restrict__ out_score, int32_t *__restrict__ big_rows,
-                      int32_t *__restrict__ n_big) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= n_rows) return;
-    const int64_t s0 = row_start[r];
-    const int m = (int)(row_start[r + 1] - s0);
-    if (m == 0) return;
-    if (m > 32) {
-        if (lane == 0) big_rows[atomicAdd(n_big, 1)] = (int32_t)r;
-        return;
-    }
-    uint64_t key = ~0ull;
-    int32_t col = -1;
-    double sc = 0.0;
-    if (lane < m) {
-        sc = b_score[s0 + lane];
-        col = b_col[s0 + lane];
-        key = score_key_desc(sc);
-    }
-    // bitonic sort over the 32 lanes, ascending in (key, -col); idle lanes hold the largest key and sink to the end
+// ascending bitonic sort of one (key, col, score) element per lane over (key, column descending)
+__device__ __forceinline__ void warp_sort32(uint64_t &key, int32_t &col, double &sc, int lane) {
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
@@ -92,6 +70,70 @@ sel_rows_small_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restri
             const bool mine_first = sel_before(key, col, ok, oc);
             const bool keep = (lower == up) ? mine_first : !mine_first;
             if (!keep && !(key == ok && col == oc)) { key = ok; col = oc; sc = os; }
+        }
+    }
+}
+
+// One warp per row.  STREAM = true (top_n <= 32): a row of any length is taken 32 survivors at a time; the warp keeps
+// the best 32 seen so far, sorted, one per lane — sort the new 32, C_i = min(best_i, new_{31-i}) are the best 32 of the
+// union as a bitonic sequence, five merge stages sort them.  STREAM = false: rows with more than 32 survivors are
+// appended to `big_rows` for the shared-memory kernels.
+template <bool STREAM>
+__global__ void __launch_bounds__(256)
+sel_rows_small_kernel(int64_t n_rows, int64_t row_begin, const int64_t *__restrict__ row_start,
+                      const int32_t *__restrict__ b_col, const double *__restrict__ b_score, int top_n,
+                      const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_row,
+                      int32_t *__restrict__ out_col, double *__restrict__ out_score, int32_t *__restrict__ big_rows,
+                      int32_t *__restrict__ n_big) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int64_t s0 = row_start[r];
+    const int m = (int)(row_start[r + 1] - s0);
+    if (m == 0) return;
+    if (!STREAM && m > 32) {
+        if (lane == 0) big_rows[atomicAdd(n_big, 1)] = (int32_t)r;
+        return;
+    }
+    uint64_t key = ~0ull;
+    int32_t col = -1;
+    double sc = 0.0;
+    if (lane < m) {
+        sc = b_score[s0 + lane];
+        col = b_col[s0 + lane];
+        key = score_key_desc(sc);
+    }
+    // idle lanes hold the largest key and sink to the end
+    warp_sort32(key, col, sc, lane);
+    if (STREAM) {
+        for (int base = 32; base < m; base += 32) {
+            uint64_t nk = ~0ull;
+            int32_t nc = -1;
+            double ns = 0.0;
+            if (base + lane < m) {
+                ns = b_score[s0 + base + lane];
+                nc = b_col[s0 + base + lane];
+                nk = score_key_desc(ns);
+            }
+            // nothing in this piece beats the current 32nd best: skip it
+            const uint64_t worst_k = __shfl_sync(FULL, key, 31);
+            const int32_t worst_c = __shfl_sync(FULL, col, 31);
+            if (!__any_sync(FULL, sel_before(nk, nc, worst_k, worst_c))) continue;
+            warp_sort32(nk, nc, ns, lane);
+            const uint64_t rk = __shfl_sync(FULL, nk, 31 - lane);
+            const int32_t rc = __shfl_sync(FULL, nc, 31 - lane);
+            const double rs = __shfl_sync(FULL, ns, 31 - lane);
+            if (sel_before(rk, rc, key, col)) { key = rk; col = rc; sc = rs; }
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {              // bitonic merge, ascending
+                const uint64_t ok = __shfl_xor_sync(FULL, key, j);
+                const int32_t oc = __shfl_xor_sync(FULL, col, j);
+                const double os = __shfl_xor_sync(FULL, sc, j);
+                const bool lower = ((lane & j) == 0);
+                const bool mine_first = sel_before(key, col, ok, oc);
+                const bool keep = lower ? mine_first : !mine_first;
+                if (!keep && !(key == ok && col == oc)) { key = ok; col = oc; sc = os; }
+            }
         }
     }
     const int kk = m < top_n ? m : top_n;
@@ -311,20 +353,26 @@ int sg_topn_select_rows(int64_t n_cand, const int32_t *cand_row, const int32_t *
     sel_scatter_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(n_cand, cand_row, cand_col, score, row_begin,
                                                                         row_start, fill, b_col, b_score);
     SG_LAUNCH_CHECK();
-    sel_rows_small_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, row_begin, row_start, b_col, b_score,
-                                                                       top_n, out_indptr, out_row, out_col, out_score,
-                                                                       big_rows, n_big);
-    SG_LAUNCH_CHECK();
-    int dev = 0, n_sm = 0;
-    SG_CUDA_TRY(cudaGetDevice(&dev));
-    SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    sel_rows_mid_kernel<<<(unsigned)(n_sm * 2), SEL_MID_WARPS * 32, 0, st>>>(row_begin, row_start, b_col, b_score, top_n,
-                                                                            out_indptr, out_row, out_col, out_score,
-                                                                            big_rows, n_big);
-    SG_LAUNCH_CHECK();
-    sel_rows_big_kernel<<<(unsigned)(n_sm * 2), 256, 0, st>>>(row_begin, row_start, b_col, b_score, top_n, out_indptr,
-                                                             out_row, out_col, out_score, big_rows, n_big);
-    SG_LAUNCH_CHECK();
+    if (top_n <= 32) {
+        // the common case (max_n_matches defaults to 20): every row, whatever its length, by one warp
+        sel_rows_small_kernel<true><<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(
+            n_rows, row_begin, row_start, b_col, b_score, top_n, out_indptr, out_row, out_col, out_score, big_rows, n_big);
+        SG_LAUNCH_CHECK();
+    } else {
+        sel_rows_small_kernel<false><<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(
+            n_rows, row_begin, row_start, b_col, b_score, top_n, out_indptr, out_row, out_col, out_score, big_rows, n_big);
+        SG_LAUNCH_CHECK();
+        int dev = 0, n_sm = 0;
+        SG_CUDA_TRY(cudaGetDevice(&dev));
+        SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        sel_rows_mid_kernel<<<(unsigned)(n_sm * 2), SEL_MID_WARPS * 32, 0, st>>>(row_begin, row_start, b_col, b_score,
+                                                                                top_n, out_indptr, out_row, out_col,
+                                                                                out_score, big_rows, n_big);
+        SG_LAUNCH_CHECK();
+        sel_rows_big_kernel<<<(unsigned)(n_sm * 2), 256, 0, st>>>(row_begin, row_start, b_col, b_score, top_n, out_indptr,
+                                                                 out_row, out_col, out_score, big_rows, n_big);
+        SG_LAUNCH_CHECK();
+    }
     sel_finish_kernel<<<1, 32, 0, st>>>(n_rows, out_indptr, out_nnz);
     SG_LAUNCH_CHECK();
     return SG_OK;

@@ -102,7 +102,7 @@ def test_config2_100k_all_pairs_equal_cpu_port():
     pre = D.cossim_topn(A, A, 20, 0.8).host_triples()
     got = sg._matches_list
     par = bench_cpu.compare(job, pre, (got.master_side.to_numpy(), got.dupe_side.to_numpy(), got.similarity.to_numpy()))
-    assert par["ok"] and par["match_list"]["pairs_ref"] > 500_000, par
+    assert par["ok"] and par["match_list"]["pairs_ref"] > 400_000, par
 
 
 def test_config4_shape_two_series_all_pairs_equal_cpu_port():
