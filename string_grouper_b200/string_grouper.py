@@ -693,7 +693,9 @@ def _side_columns(series, positions, default_name, drop_index, prefix, mirror, v
     if not (drop_index or (index.nlevels == 1 and index.name is None and name != 'index')):
         return None
     taken = series.array.take(positions) if values is None else values
-    out = [(f"{prefix}{name}", taken)]
+    # keep the Series' own dtype (an object column must stay object: the DataFrame constructor would otherwise infer
+    # `str` from it — a different dtype than the reference's `iloc`, and a full conversion pass over the result)
+    out = [(f"{prefix}{name}", pd.Series(taken, dtype=series.dtype, copy=False))]
     if drop_index:
         return out
     if isinstance(index, pd.RangeIndex):
