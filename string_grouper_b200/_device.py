@@ -19,7 +19,7 @@ LAUNCH_COUNTS = {"postings": 0, "candidates": 0, "rescore": 0, "select": 0, "sym
 
 TRANSFER_BYTES = {"d2h": 0, "h2d": 0}      # bytes moved by the bulk copies (bench.py e2e accounting)
 
-DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 512-byte accumulator tiles (256 columns of u16)
+DEFAULT_TILE_W = int(os.environ.get("SG_B200_TILE_W", "0"))         # 0: 256 (u16) columns per tile, 128 for large right matrices
 DEFAULT_WARPS = int(os.environ.get("SG_B200_WARPS", "8"))           # 8 warps x 5 CTAs at 48 registers (no spills)
 GROUP_BYTES = int(os.environ.get("SG_B200_GROUP_MB", "12")) << 20   # posting bytes one column-tile group may hold
 CAND_MARGIN = 1.5e-3   # candidates: fp16 posting weights (<= 4.9e-4) + fp32 accumulation; all are re-scored exactly
@@ -400,7 +400,10 @@ def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
     point): narrow tiles make the block-max test skip most (row, tile) pairs, and the test itself costs a
     fraction of an instruction per pair."""
     warps = int(warps or DEFAULT_WARPS)
-    tile_w = int(tile_w or DEFAULT_TILE_W) or 512 // acc_bytes
+    # measured on B200 (profiles/r2_notes.md): 128-column tiles win from a few 10^5 right rows on (the block-max test
+    # skips more, 34.5 vs 38.0 ms at 663k), 256-column tiles below (1.4 vs 1.8 ms at 100k: fewer directory entries)
+    auto_w = 128 if (acc_bytes == 4 or int(n_right) >= 400_000) else 256
+    tile_w = int(tile_w or DEFAULT_TILE_W) or auto_w
     q = 256 // acc_bytes                               # tile bytes must be a multiple of 256
     need = ((max(int(n_right), 1) + q - 1) // q) * q
     tile_w = max(q, min(tile_w, 32768) // q * q)
