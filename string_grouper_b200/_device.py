@@ -395,14 +395,16 @@ class DeviceMatches:
     __hash__ = object.__hash__
 
 
-def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4):
+def pick_tile(n_right, tile_w=None, warps=None, acc_bytes=4, n_left=None):
     """Column-tile width and warps per CTA.  Default: 512-byte accumulator tiles (256 columns of 16-bit fixed
     point): narrow tiles make the block-max test skip most (row, tile) pairs, and the test itself costs a
     fraction of an instruction per pair."""
     warps = int(warps or DEFAULT_WARPS)
     # measured on B200 (profiles/r2_notes.md): 128-column tiles win from a few 10^5 right rows on (the block-max test
     # skips more, 34.5 vs 38.0 ms at 663k), 256-column tiles below (1.4 vs 1.8 ms at 100k: fewer directory entries)
-    auto_w = 128 if (acc_bytes == 4 or int(n_right) >= 400_000) else 256
+    # (the finer directory costs ~0.6 ms more to build: not worth it for a small block of left rows, e.g. one of 8 shards)
+    many_left = n_left is None or int(n_left) >= 150_000
+    auto_w = 128 if (acc_bytes == 4 or (int(n_right) >= 400_000 and many_left)) else 256
     tile_w = int(tile_w or DEFAULT_TILE_W) or auto_w
     q = 256 // acc_bytes                               # tile bytes must be a multiple of 256
     need = ((max(int(n_right), 1) + q - 1) // q) * q
@@ -514,7 +516,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         lpack = _empty(2 * A.d_indices.numel(), t.int32, dev)
         mask_words = int(L.sg_tiles_mask_words(n_right))
     else:
-        tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4)
+        tile_w, warps = pick_tile(n_right, tile_w, warps, 2 if acc == "u16" else 4, n_left=n_rows)
         # the bucket directory holds one entry per (feature, tile): widen the tiles until it stays below MAX_BUCKETS
         while (-(-n_right // tile_w)) * (B.shape[1] + 1) > MAX_BUCKETS and tile_w < 32768:
             tile_w *= 2
