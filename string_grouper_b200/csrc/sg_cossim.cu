@@ -144,81 +144,62 @@ struct AccOps<uint16_t> {
     }
 };
 
-// A bucket-directory batch of a row = 32 features, one per lane (bucket [b0, b0+len) and left weight a), applied to the
-// accumulator region:
+// One bucket-directory batch of a row (32 features, one per lane: bucket [b0, b0+len) and left weight a)
+// applied to the accumulator tile.
 //   * buckets of LONG_BUCKET postings or more: the whole warp streams one bucket at a time;
 //   * all the others are walked as ONE concatenated list, 32 postings per step whatever the bucket boundaries
 //     (after pruning a row keeps its rarer features, whose buckets hold a dozen postings per tile: one bucket
-//     per step would leave most lanes idle).  Lane -> owner by a 5-step binary search over the running
+//     per step would leave most lanes idle).  Lane -> bucket by a 5-step binary search over the running
 //     sums; two lanes of a step may meet on one column, hence shared-memory atomics.
-// Two tiles at once: lane k holds its feature's bucket in tile A ([b0A, b0A+lenA)) and in tile B; the accumulator region is
-// 2*W columns wide (tile A first).  The fixed work of a (row, tile) pair — prefix sums, owner search set-up, sweep / clear
-// of the tile — is paid once for the two tiles; `hit` becomes true when a written value exceeds its tile's threshold.
 template <typename AccT>
-__device__ __forceinline__ void apply_buckets2(AccT *__restrict__ acc, const uint32_t *__restrict__ post, int b0A,
-                                               int lenA, int b0B, int lenB, float a, int lane, int W,
-                                               typename AccOps<AccT>::val_t thrA, typename AccOps<AccT>::val_t thrB,
-                                               bool &hit) {
+__device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint32_t *__restrict__ post, int b0,
+                                              int len, float a, int lane,
+                                              typename AccOps<AccT>::val_t &seen) {
     typedef AccOps<AccT> Ops;
-    typedef typename Ops::val_t val_t;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-        const int b0 = which ? b0B : b0A, len = which ? lenB : lenA;
-        AccT *base = acc + (which ? W : 0);
-        const val_t thr = which ? thrB : thrA;
-        unsigned m = __ballot_sync(FULL, len >= LONG_BUCKET);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int s = __shfl_sync(FULL, b0, src);
-            const int e = s + __shfl_sync(FULL, len, src);
-            const float ak = __shfl_sync(FULL, a, src);
-            val_t seen = 0;
-            int p = s + lane;
-            for (; p + 96 < e; p += 128) {
-                const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
-                const val_t v0 = Ops::fma_store(base, post_c(e0), ak, post_w(e0));
-                const val_t v1 = Ops::fma_store(base, post_c(e1), ak, post_w(e1));
-                const val_t v2 = Ops::fma_store(base, post_c(e2), ak, post_w(e2));
-                const val_t v3 = Ops::fma_store(base, post_c(e3), ak, post_w(e3));
-                seen = Ops::vmax(Ops::vmax(Ops::vmax(seen, v0), Ops::vmax(v1, v2)), v3);
-            }
-            for (; p < e; p += 32) {
-                const uint32_t e0 = post[p];
-                seen = Ops::vmax(seen, Ops::fma_store(base, post_c(e0), ak, post_w(e0)));
-            }
-            hit = hit || seen > thr;
-            __syncwarp();
+    unsigned m = __ballot_sync(FULL, len >= LONG_BUCKET);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int s = __shfl_sync(FULL, b0, src);
+        const int e = s + __shfl_sync(FULL, len, src);
+        const float ak = __shfl_sync(FULL, a, src);
+        int p = s + lane;
+        for (; p + 96 < e; p += 128) {
+            const uint32_t e0 = post[p], e1 = post[p + 32], e2 = post[p + 64], e3 = post[p + 96];
+            const typename Ops::val_t v0 = Ops::fma_store(acc, post_c(e0), ak, post_w(e0));
+            const typename Ops::val_t v1 = Ops::fma_store(acc, post_c(e1), ak, post_w(e1));
+            const typename Ops::val_t v2 = Ops::fma_store(acc, post_c(e2), ak, post_w(e2));
+            const typename Ops::val_t v3 = Ops::fma_store(acc, post_c(e3), ak, post_w(e3));
+            seen = Ops::vmax(Ops::vmax(Ops::vmax(seen, v0), Ops::vmax(v1, v2)), v3);
         }
+        for (; p < e; p += 32) {
+            const uint32_t e0 = post[p];
+            seen = Ops::vmax(seen, Ops::fma_store(acc, post_c(e0), ak, post_w(e0)));
+        }
+        __syncwarp();
     }
-    // one concatenated list over the short buckets of both tiles: lane k contributes lnA + lnB consecutive positions
-    const int lnA = lenA >= LONG_BUCKET ? 0 : lenA, lnB = lenB >= LONG_BUCKET ? 0 : lenB;
-    int incl = lnA + lnB;
+    // the concatenated walk over the remaining buckets
+    const int ln = len >= LONG_BUCKET ? 0 : len;
+    int incl = ln;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int up = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += up;
     }
     const int total = __shfl_sync(FULL, incl, 31);
-    const int start = incl - (lnA + lnB);
-    const int split = start + lnA;                 // positions [start, split) are tile A's, [split, incl) tile B's
-    const int dA = b0A - start, dB = b0B - split;  // posting index = d + position
+    const int d = b0 - (incl - ln);                    // posting index = d + position in the concatenated list
     for (int item = lane; item - lane < total; item += 32) {
-        int k = 0;                                 // number of lanes whose positions end at or before `item`
+        int k = 0;                                     // number of buckets that end at or before `item`
 #pragma unroll
         for (int st = 16; st; st >>= 1) {
             const int v = __shfl_sync(FULL, incl, k + st - 1);
             if (v <= item) k += st;
         }
-        const int spk = __shfl_sync(FULL, split, k);
-        const int dAk = __shfl_sync(FULL, dA, k);
-        const int dBk = __shfl_sync(FULL, dB, k);
+        const int dk = __shfl_sync(FULL, d, k);
         const float ak = __shfl_sync(FULL, a, k);
         if (item < total) {
-            const bool inB = item >= spk;
-            const uint32_t e0 = post[(inB ? dBk : dAk) + item];
-            const val_t v = Ops::atomic_add(acc + (inB ? W : 0), post_c(e0), ak, post_w(e0));
-            hit = hit || v > (inB ? thrB : thrA);
+            const uint32_t e0 = post[dk + item];
+            seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e0), ak, post_w(e0)));
         }
     }
     __syncwarp();
@@ -251,12 +232,12 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    AccT *acc = reinterpret_cast<AccT *>(smem_raw) + (size_t)warp * 2 * W;     // two tiles side by side
+    AccT *acc = reinterpret_cast<AccT *>(smem_raw) + (size_t)warp * W;
     uint4 *acc16 = reinterpret_cast<uint4 *>(acc);
     const int n16 = W / Ops::PER16;                         // 16-byte vectors per tile
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
-    for (int c = lane; c < 2 * n16; c += 32) acc16[c] = zero4;
+    for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
     __syncwarp();
 
     // Work item = (column-tile group, left row), groups outermost: at any moment every CTA of the grid streams
@@ -322,64 +303,50 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                 m_even = __ballot_sync(FULL, t0 < t_end);
                 m_odd = __ballot_sync(FULL, t0 + 1 < t_end);
             }
-            // ---- walk the surviving tiles TWO at a time (one accumulator region of 2*W columns); the directory
-            // entries of the next two are fetched ahead
-            auto pop = [&]() {
-                int t = -1;
-                if (m_even) { t = tb + 2 * (__ffs(m_even) - 1); m_even &= m_even - 1; }
-                else if (m_odd) { t = tb + 2 * (__ffs(m_odd) - 1) + 1; m_odd &= m_odd - 1; }
-                return t;
-            };
-            int tA = pop();
-            int tB = tA >= 0 ? pop() : -1;
-            int2 dA_cur = make_int2(0, 0), dB_cur = make_int2(0, 0);
-            if (lane < nf) {
-                if (tA >= 0) dA_cur = drow[tA];
-                if (tB >= 0) dB_cur = drow[tB];
-            }
-            while (tA >= 0) {
-                const int tA_next = pop();
-                const int tB_next = tA_next >= 0 ? pop() : -1;
-                int2 dA_next = make_int2(0, 0), dB_next = make_int2(0, 0);
-                if (lane < nf) {
-                    if (tA_next >= 0) dA_next = drow[tA_next];
-                    if (tB_next >= 0) dB_next = drow[tB_next];
-                }
-                const float thrA_f = xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[tA], thr_r), 0.f) : thr_r;
-                const float thrB_f = (tB >= 0 && xp > 0.f) ? fmaxf(fmaf(-xp, tile_bound[tB], thr_r), 0.f) : thr_r;
-                const val_t thrA_c = Ops::threshold(thrA_f), thrB_c = Ops::threshold(thrB_f);
-                bool hit = false;        // a value written into the region exceeded its tile's candidate threshold
-                apply_buckets2<AccT>(acc, post, dA_cur.x, dir_len(dA_cur), dB_cur.x, dir_len(dB_cur), a0, lane, W,
-                                     thrA_c, thrB_c, hit);
+            // ---- walk the surviving tiles; the directory entry of the next one is fetched ahead
+            int t = -1;
+            if (m_even) { t = tb + 2 * (__ffs(m_even) - 1); m_even &= m_even - 1; }
+            else if (m_odd) { t = tb + 2 * (__ffs(m_odd) - 1) + 1; m_odd &= m_odd - 1; }
+            int2 d_cur = make_int2(0, 0);
+            if (t >= 0 && lane < nf) d_cur = drow[t];
+            while (t >= 0) {
+                int t_next = -1;
+                if (m_even) { t_next = tb + 2 * (__ffs(m_even) - 1); m_even &= m_even - 1; }
+                else if (m_odd) { t_next = tb + 2 * (__ffs(m_odd) - 1) + 1; m_odd &= m_odd - 1; }
+                int2 d_next = make_int2(0, 0);
+                if (t_next >= 0 && lane < nf) d_next = drow[t_next];
+
+                const float thr_f = xp > 0.f ? fmaxf(fmaf(-xp, tile_bound[t], thr_r), 0.f) : thr_r;
+                const val_t thr_c = Ops::threshold(thr_f);
+                val_t seen = 0;        // largest value this lane wrote into the tile
+                apply_buckets<AccT>(acc, post, d_cur.x, dir_len(d_cur), a0, lane, seen);
                 if (nf > 32) {
                     for (int base = 32; base < nf; base += 32) {
                         const int k = base + lane;
-                        int2 ea = make_int2(0, 0), eb = make_int2(0, 0);
+                        int b0 = 0, len = 0;
                         float a = 0.f;
                         if (k < nf) {
-                            const int2 *dr = bdir + a_idx[p0 + k] * n_tiles;
+                            const int2 d = bdir[a_idx[p0 + k] * n_tiles + t];
                             a = Ops::left_weight(a_val[p0 + k] * a_scale);
-                            ea = dr[tA];
-                            if (tB >= 0) eb = dr[tB];
+                            b0 = d.x;
+                            len = dir_len(d);
                         }
-                        apply_buckets2<AccT>(acc, post, ea.x, dir_len(ea), eb.x, dir_len(eb), a, lane, W, thrA_c, thrB_c,
-                                             hit);
+                        apply_buckets<AccT>(acc, post, b0, len, a, lane, seen);
                     }
                 }
-                if (!__any_sync(FULL, hit)) {
-                    // No value written into the two tiles exceeded its threshold: clearing is enough
-                    for (int c = lane; c < 2 * n16; c += 32) acc16[c] = zero4;
+                if (!__any_sync(FULL, seen > thr_c)) {
+                    // No value written into this tile exceeded the candidate threshold: clearing is enough
+                    for (int c = lane; c < n16; c += 32) acc16[c] = zero4;
                 } else {
-                    // sweep: report scores above the candidate threshold, clear the region; one atomic per warp step
-                    for (int c0 = 0; c0 < 2 * n16; c0 += 32) {
+                    // sweep: report scores above the candidate threshold, clear the tile; one atomic per warp step
+                    for (int c0 = 0; c0 < n16; c0 += 32) {
                         const int c = c0 + lane;
                         unsigned m = 0;
-                        const bool inB = c >= n16;
-                        if (c < 2 * n16) {
+                        if (c < n16) {
                             const uint4 v = acc16[c];
                             if (v.x | v.y | v.z | v.w) {
                                 acc16[c] = zero4;
-                                m = Ops::above(v, inB ? thrB_c : thrA_c);
+                                m = Ops::above(v, thr_c);
                             }
                         }
                         if (__any_sync(FULL, m != 0)) {
@@ -397,7 +364,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                                 const int i = __ffs(m) - 1;
                                 m &= m - 1;
                                 if (slot < cap) {
-                                    const int col = (inB ? tB * W + (c - n16) * Ops::PER16 : tA * W + c * Ops::PER16) + i;
+                                    const int col = t * W + c * Ops::PER16 + i;
                                     cand_row[slot] = (int32_t)row;
                                     cand_col[slot] = perm_b ? perm_b[col] : col;
                                 }
@@ -407,8 +374,8 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     }
                 }
                 __syncwarp();
-                tA = tA_next; tB = tB_next;
-                dA_cur = dA_next; dB_cur = dB_next;
+                t = t_next;
+                d_cur = d_next;
             }
         }
     }
@@ -700,7 +667,7 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
                              int32_t *cand_row, int32_t *cand_col,
                              int64_t cand_cap, unsigned long long *cand_count, unsigned long long *row_queue,
                              int n_sm, cudaStream_t st) {
-    const size_t smem = (size_t)NW * 2 * tile_w * sizeof(AccT);      // two accumulator tiles per warp
+    const size_t smem = (size_t)NW * tile_w * sizeof(AccT);
     SG_CUDA_TRY(cudaFuncSetAttribute(cossim_candidates_kernel<NW, AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     const int64_t T = sg_num_tiles(n_right, tile_w);
@@ -749,9 +716,9 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
     SG_CUDA_TRY(cudaGetDevice(&dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     SG_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if ((size_t)warps_per_cta * 2 * tile_w * acc_bytes > (size_t)smem_optin)
-        return fail(SG_ERR_INVALID, "warps_per_cta*2*tile_w*%d = %zu exceeds %d bytes of shared memory", acc_bytes,
-                    (size_t)warps_per_cta * 2 * tile_w * acc_bytes, smem_optin);
+    if ((size_t)warps_per_cta * tile_w * acc_bytes > (size_t)smem_optin)
+        return fail(SG_ERR_INVALID, "warps_per_cta*tile_w*%d = %zu exceeds %d bytes of shared memory", acc_bytes,
+                    (size_t)warps_per_cta * tile_w * acc_bytes, smem_optin);
 #define SG_ARGS                                                                                              \
     a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, bucket_maxw, \
         postings, perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, pruned_norm_row,      \
