@@ -81,6 +81,12 @@ __device__ __forceinline__ float dir_maxw(int2 d) {
 // candidate generation
 // ---------------------------------------------------------------------------
 constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
+#ifndef SG_WALK_MLP
+#define SG_WALK_MLP 2            // steps of the concatenated walk whose posting loads are in flight together
+#endif
+#ifndef SG_FILTER_MLP
+#define SG_FILTER_MLP 4          // block-maxima loads in flight per lane in the block-max test
+#endif
 
 // Resident CTAs per SM the register allocation is made for (the accumulator tiles are small, registers decide):
 // 32 warps/CTA x 2 = 64 warps at 32 registers; 16 x 3 = 48 warps at 40; 8 x 5 = 40 warps at 48; 4 x 8 = 32 warps at 64.
@@ -188,18 +194,29 @@ __device__ __forceinline__ void apply_buckets(AccT *__restrict__ acc, const uint
     }
     const int total = __shfl_sync(FULL, incl, 31);
     const int d = b0 - (incl - ln);                    // posting index = d + position in the concatenated list
-    for (int item = lane; item - lane < total; item += 32) {
-        int k = 0;                                     // number of buckets that end at or before `item`
+    // SG_WALK_MLP steps at a time: the posting loads of all of them are issued before the first accumulator update
+    // (the kernel is bound by the latency of these L2 loads, not by issue slots)
+    for (int base = 0; base < total; base += 32 * SG_WALK_MLP) {
+        uint32_t e[SG_WALK_MLP];
+        float ak[SG_WALK_MLP];
 #pragma unroll
-        for (int st = 16; st; st >>= 1) {
-            const int v = __shfl_sync(FULL, incl, k + st - 1);
-            if (v <= item) k += st;
+        for (int u = 0; u < SG_WALK_MLP; ++u) {
+            const int item = base + 32 * u + lane;
+            int k = 0;                                 // number of buckets that end at or before `item`
+#pragma unroll
+            for (int st = 16; st; st >>= 1) {
+                const int v = __shfl_sync(FULL, incl, k + st - 1);
+                if (v <= item) k += st;
+            }
+            const int dk = __shfl_sync(FULL, d, k);
+            ak[u] = __shfl_sync(FULL, a, k);
+            e[u] = 0u;
+            if (item < total) e[u] = post[dk + item];
         }
-        const int dk = __shfl_sync(FULL, d, k);
-        const float ak = __shfl_sync(FULL, a, k);
-        if (item < total) {
-            const uint32_t e0 = post[dk + item];
-            seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e0), ak, post_w(e0)));
+#pragma unroll
+        for (int u = 0; u < SG_WALK_MLP; ++u) {
+            const int item = base + 32 * u + lane;
+            if (item < total) seen = Ops::vmax(seen, Ops::atomic_add(acc, post_c(e[u]), ak[u], post_w(e[u])));
         }
     }
     __syncwarp();
@@ -285,11 +302,20 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
             if (nf <= 32) {
                 __half2 ub2 = __float2half2_rn(0.f);
                 const uint32_t *mrow = maxw_h + (tb >> 1) + lane;
-                for (int k = 0; k < nk; ++k) {
-                    const int fk = __shfl_sync(FULL, f0, k);
-                    const __half2 ak2 = __shfl_sync(FULL, a2, k);
-                    const uint32_t m = mrow[fk * (Tp >> 1)];
-                    ub2 = __hfma2(ak2, *reinterpret_cast<const __half2 *>(&m), ub2);
+                // SG_FILTER_MLP block-maxima loads in flight per lane
+                for (int k0 = 0; k0 < nk; k0 += SG_FILTER_MLP) {
+                    uint32_t m[SG_FILTER_MLP];
+                    __half2 ak2[SG_FILTER_MLP];
+#pragma unroll
+                    for (int u = 0; u < SG_FILTER_MLP; ++u) {
+                        const int kk = k0 + u;
+                        const int fk = __shfl_sync(FULL, f0, kk & 31);
+                        ak2[u] = __shfl_sync(FULL, a2, kk & 31);
+                        m[u] = kk < nk ? mrow[fk * (Tp >> 1)] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < SG_FILTER_MLP; ++u)
+                        ub2 = __hfma2(ak2[u], *reinterpret_cast<const __half2 *>(&m[u]), ub2);
                 }
                 const float2 ub = __half22float2(ub2);
                 const float2 tb2 = reinterpret_cast<const float2 *>(tile_bound)[(tb >> 1) + lane];

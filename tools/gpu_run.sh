@@ -1,6 +1,9 @@
-timeout 400 python tests/gpu_k2_compare.py 663000 both 3 > gpurun_out/r2l_cmp663k.log 2>&1; echo "rc663k=$?"
-tail -8 gpurun_out/r2l_cmp663k.log
-timeout 300 python tests/gpu_k2_compare.py 100000 both 2 > gpurun_out/r2l_cmp100k.log 2>&1; echo "rc100k=$?"
-tail -3 gpurun_out/r2l_cmp100k.log
-timeout 900 python -m pytest tests/test_gpu_cossim.py tests/test_gpu_compat.py tests/test_gpu_fullsize.py::test_full_size_kernels_and_pruning_levels_agree -q -m gpu -x > gpurun_out/r2l_tests.log 2>&1; echo "rctests=$?"
-tail -6 gpurun_out/r2l_tests.log
+cd string_grouper_b200/csrc
+for cfg in "1 1" "2 4" "4 8" "1 8" "4 1" "2 8"; do
+set -- $cfg
+touch sg_cossim.cu; make -s EXTRA="-DSG_WALK_MLP=$1 -DSG_FILTER_MLP=$2" 2>&1 | grep -E "error" 
+cd ../..
+echo "== walk=$1 filter=$2"
+timeout 300 python tests/gpu_k2_compare.py 663000 row 3 2>&1 | tail -2 | cut -c1-110
+cd string_grouper_b200/csrc
+done
