@@ -82,10 +82,12 @@ __device__ __forceinline__ float dir_maxw(int2 d) {
 // ---------------------------------------------------------------------------
 constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
 #ifndef SG_WALK_MLP
-#define SG_WALK_MLP 2            // steps of the concatenated walk whose posting loads are in flight together
+#define SG_WALK_MLP 1            // steps of the concatenated walk whose posting loads are in flight together
 #endif
 #ifndef SG_FILTER_MLP
-#define SG_FILTER_MLP 4          // block-maxima loads in flight per lane in the block-max test
+#define SG_FILTER_MLP 1          // block-maxima loads in flight per lane in the block-max test
+// Measured on B200, 663k rows (profiles/r2_notes.md): 1/1 34.3 ms; walk 2 / filter 4: 38.0; 4 / 8: 41.5; 1 / 8: 38.8; 4 / 1: 36.6.
+// With 40 resident warps the load latency is already covered; the extra registers / predicated work only cost issue slots.
 #endif
 
 // Resident CTAs per SM the register allocation is made for (the accumulator tiles are small, registers decide):
