@@ -27,6 +27,7 @@ for kernel in (["tiles", "row"] if which == "both" else [which]):
         print("%s rep %d: cossim_topn %.1f ms, candidates launch(es) %.2f ms, cand=%d above=%d nnz=%d pairs=%s postings=%s stage=%s prune=%s select=%s" % (
             kernel, rep, tk * 1e3, kms, st["n_candidates"], st["n_above_threshold"], got.nnz, st.get("pairs_walked"),
             st.get("postings_walked"), st.get("stage_bytes"), st.get("prune"), st.get("select")), flush=True)
+        print("   phases ms:", {k: round(v, 2) for k, v in D.phases_ms(st).items()}, flush=True)
     res[kernel] = got.host_triples()
 if len(res) == 2:
     a, b = res["tiles"], res["row"]
