@@ -81,9 +81,6 @@ __device__ __forceinline__ float dir_maxw(int2 d) {
 // candidate generation
 // ---------------------------------------------------------------------------
 constexpr int LONG_BUCKET = 64;  // buckets from this length on are streamed by the whole warp, one at a time
-#ifndef SG_RESCORE_SEARCH
-#define SG_RESCORE_SEARCH 1      // exact re-score: signature test + binary search instead of the two-pointer merge
-#endif
 #ifndef SG_WALK_MLP
 #define SG_WALK_MLP 1            // steps of the concatenated walk whose posting loads are in flight together
 #endif
@@ -428,41 +425,12 @@ struct ExactOps<float> {
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 };
 
-// Same sum as merge_dot — the products of the common features added in ascending feature order, multiply and add
-// rounded separately — without the serial two-pointer chain: the features of the right row are tested against a 64-bit
-// signature of the left row (feature id mod 64) and only the survivors (the common features plus ~25 % false
-// positives) are looked up by binary search in the left row, whose few cache lines are shared by the neighbouring
-// candidates (same left row).  Rows longer than 64 features fall back to the merge.
-template <typename T>
-__device__ __forceinline__ T search_dot(const int32_t *__restrict__ ai, const T *__restrict__ av, int64_t pa,
-                                        int64_t ea, const int32_t *__restrict__ bi,
-                                        const T *__restrict__ bv, int64_t pb, int64_t eb) {
-    T sum = (T)0;
-    unsigned long long sig = 0ull;
-    for (int64_t p = pa; p < ea; ++p) sig |= 1ull << (ai[p] & 63);
-    const int64_t first = ai[pa], last = ai[ea - 1];
-    for (int64_t p = pb; p < eb; ++p) {
-        const int32_t f = bi[p];
-        if (f < first || f > last || !((sig >> (f & 63)) & 1ull)) continue;
-        int64_t lo = pa, hi = ea;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (ai[mid] < f) lo = mid + 1; else hi = mid;
-        }
-        if (lo < ea && ai[lo] == f) sum = ExactOps<T>::add(sum, ExactOps<T>::mul(av[lo], bv[p]));
-    }
-    return sum;
-}
-
 template <typename T>
 __device__ __forceinline__ T merge_dot(const int32_t *__restrict__ ai, const T *__restrict__ av, int64_t pa,
                                        int64_t ea, const int32_t *__restrict__ bi,
                                        const T *__restrict__ bv, int64_t pb, int64_t eb) {
     T sum = (T)0;
     if (pa >= ea || pb >= eb) return sum;
-#if SG_RESCORE_SEARCH
-    if (ea - pa <= 64 && eb - pb <= 64) return search_dot<T>(ai, av, pa, ea, bi, bv, pb, eb);
-#endif
     int32_t fa = ai[pa], fb = bi[pb];
     for (;;) {
         if (fa == fb) {
