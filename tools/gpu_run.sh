@@ -1,9 +1,5 @@
-cd string_grouper_b200/csrc
-for v in 0 1; do
-touch sg_cossim.cu; make -s EXTRA="-DSG_RESCORE_SEARCH=$v" 2>&1 | grep -E "error"
-cd ../..
-echo "== rescore search=$v"
-timeout 300 python tests/gpu_k2_compare.py 663000 row 3 2>&1 | grep phases | tail -2
-timeout 300 python tests/gpu_k2_compare.py 100000 row 3 2>&1 | grep phases | tail -1
-cd string_grouper_b200/csrc
-done
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; echo "rcsmoke=$?"; tail -1 gpurun_out/r2_final_smoke.log
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2_tests_final2.log 2>&1; echo "rctests=$?"
+tail -4 gpurun_out/r2_tests_final2.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_1gpu_final.json 2> gpurun_out/r2_bench_1gpu_final.err; echo "rcbench=$?"
+tail -c 300 gpurun_out/r2_bench_1gpu_final.err
