@@ -97,6 +97,10 @@ int sg_tfidf_finalize(const int64_t *offsets /*[dev]*/, int64_t n_docs,
 /* keys_out[c] = packed n-gram of column c (sorted vocabulary), V entries. */
 int sg_tfidf_vocab_keys(const int32_t *df_table /*[dev]*/, const int32_t *rank_table /*[dev]*/, int ngram,
                         uint32_t *keys_out /*[dev] V*/, void *stream);
+/* df_out[c] = document frequency of column c over the fitted rows (TfidfVectorizer's df; equals sg_feature_df of
+ * the matrix when it holds exactly the fitted rows). */
+int sg_tfidf_vocab_df(const int32_t *df_table /*[dev]*/, const int32_t *rank_table /*[dev]*/, int ngram,
+                      int32_t *df_out /*[dev] V*/, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * K1, general form (csrc/sg_tfidf64.cu): 64-bit n-gram keys and a sort-based vocabulary — ngram_size >= 4 and text
@@ -350,8 +354,9 @@ int sg_topn_merge(int64_t n_entries, const int32_t *row, const int32_t *col, con
  * ------------------------------------------------------------------------- */
 size_t sg_order_workspace_bytes(int64_t n_rows, int64_t n_cols);
 /* hrank[n_cols] int8: rank among the n_heavy (<= 64) most frequent features of the matrix, else -1 */
-int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices, int n_heavy,
-                      int8_t *hrank /*[dev]*/, void *ws, size_t ws_bytes, void *stream);
+int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices,
+                      const int32_t *df /*[dev] n_cols, optional: sg_feature_df of the matrix, else counted here*/,
+                      int n_heavy, int8_t *hrank /*[dev]*/, void *ws, size_t ws_bytes, void *stream);
 /* perm[i] = id of the i-th row of [row_begin,row_end) in signature order; rank = inverse (relative ids).
  * With `row_norm` (per row of the range, sg_heavy_norms) the 5-bit quantisation of row_norm*norm_scale leads the
  * sort key, so that rows of similar heavy norm share column tiles (see sg_tile_bounds). */

@@ -31,6 +31,8 @@ ACC_DTYPE = os.environ.get("SG_B200_ACC", "u16")                    # accumulato
 MAX_CAND_DENSITY = float(os.environ.get("SG_B200_MAX_CAND_DENSITY", "1.5e-3"))   # candidates per (row, column) pair
 MAX_BUCKETS = int(os.environ.get("SG_B200_MAX_BUCKETS", str(400_000_000)))       # directory entries (22 B each)
 CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
+# up to this many (left row, right row) pairs the candidates kernel is launched without a sizing pass (see cossim_topn)
+OPTIMISTIC_PAIRS = float(os.environ.get("SG_B200_OPTIMISTIC_PAIRS", "5e11"))
 # K2 formulation: "row" (the default) = one warp per left row over L2-resident posting buckets (csrc/sg_cossim.cu; also
 # the general path: negative values, norms above 1, near-zero thresholds); "tiles" = right tiles staged through TMA into
 # shared memory (csrc/sg_tiles.cu), for L2-normalised non-negative operands.  Measured on B200 at 663k rows the row kernel
@@ -222,9 +224,9 @@ def heavy_features(B):
     hrank = _empty(n_cols, t.int8, B.device)
     ws_bytes = int(L.sg_order_workspace_bytes(n_rows, n_cols))
     ws = _empty(ws_bytes, t.uint8, B.device)
-    _lib.check(L.sg_heavy_features(n_rows, n_cols, _ptr(B.d_indptr), _ptr(B.d_indices), 64, _ptr(hrank), _ptr(ws),
-                                   ws_bytes, _stream()))
-    LAUNCH_COUNTS["order"] += 4
+    _lib.check(L.sg_heavy_features(n_rows, n_cols, _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(feature_df(B)), 64,
+                                   _ptr(hrank), _ptr(ws), ws_bytes, _stream()))
+    LAUNCH_COUNTS["order"] += 3
     return hrank
 
 
@@ -573,24 +575,72 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     levels = [prune]
     if prune_auto and prune > 0.0 and thr_c > 0.0:
         levels = [prune, 0.75 * prune, 0.5 * prune, 0.25 * prune, 0.0]
-    sample = None
-    if not os.environ.get("SG_B200_CAND_CAP") and n_rows >= 65536:
-        stride = max(64, n_rows // 8192)
-        sample = perm_a[:n_rows:stride].contiguous()
-    est = None
-    for level in levels:
+
+    def prepare(level):
         if (level > 0.0 and thr_c > 0.0) or margin_pf > 0.0:
             pruned["arrays"] = prune_left(A, B, hrank, row_begin, row_end, float(threshold), margin, margin_pf,
                                           level if thr_c > 0.0 else 0.0)
         else:
             pruned["arrays"] = (A.d_indices, A.d_val32, None, None, None)
-        prune = level
-        if sample is None:
-            break
-        launch(sample, row_begin, row_begin + int(sample.numel()), dummy, dummy, 0)
-        est = int(counters[0].item()) * stride
-        if est <= MAX_CAND_DENSITY * n_rows * n_right:
-            break
+
+    def timed_launch(perm, rb, re_, row_buf, col_buf, capacity):
+        if _timed(stats):
+            ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            ev0.record()
+        launch(perm, rb, re_, row_buf, col_buf, capacity)
+        if _timed(stats):
+            ev1.record()
+            stats.setdefault("candidate_events", []).append((ev0, ev1))
+        head = counters[:4].cpu().numpy()
+        if use_tiles and stats is not None:
+            stats["pairs_walked"] = stats.get("pairs_walked", 0) + int(head[2])
+            stats["postings_walked"] = stats.get("postings_walked", 0) + int(head[3])
+        return int(head[0])
+
+    fixed_cap = bool(os.environ.get("SG_B200_CAND_CAP"))
+    sample = None
+    if not fixed_cap and n_rows >= 65536:
+        stride = max(64, n_rows // 8192)
+        sample = perm_a[:n_rows:stride].contiguous()
+    est = None
+    first = None          # (cand_row, cand_col, n_cand) of a whole-range launch that needed no sizing pass
+    search = True
+    dense = MAX_CAND_DENSITY * n_rows * n_right
+    # The sizing pass is latency-bound (a few thousand rows against every column tile, cold: 2-3 ms whatever the
+    # shard).  While a wasted launch costs no more than a few tens of ms, launch everything at once at the first
+    # level into buffers of the density limit; only an overflow or a count above the limit falls back to the
+    # sample / level search / row chunks below, and then the exact count of the first level is already known.
+    if not fixed_cap and float(n_rows) * float(n_right) <= OPTIMISTIC_PAIRS:
+        prune = levels[0]
+        prepare(prune)
+        cap0 = int(min(int(dense) + (1 << 22), CAND_CHUNK))
+        cand_row0 = _empty(cap0, t.int32, dev)
+        cand_col0 = _empty(cap0, t.int32, dev)
+        mark(stats, "prune_sample")
+        n0 = timed_launch(perm_a, row_begin, row_end, cand_row0, cand_col0, cap0)
+        mark(stats, "candidates")
+        too_dense = len(levels) > 1 and sample is not None and n0 > dense
+        if n0 <= cap0 and not too_dense:
+            first = (cand_row0, cand_col0, n0)
+            search = False
+        else:
+            del cand_row0, cand_col0
+            if _timed(stats):
+                stats["wasted_launch"] = True
+            if too_dense:
+                levels = levels[1:]
+            else:
+                est, search = n0, False          # stay at this level: chunks / buffers from the exact count
+    if search:
+        for level in levels:
+            prepare(level)
+            prune = level
+            if sample is None:
+                break
+            launch(sample, row_begin, row_begin + int(sample.numel()), dummy, dummy, 0)
+            est = int(counters[0].item()) * stride
+            if est <= dense:
+                break
     l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
     mark(stats, "prune_sample")
     if stats is not None:
@@ -621,20 +671,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         if est is not None:
             cap = min(max(int(1.3 * est * (hi - lo) / n_rows) + (1 << 22), 1 << 22), 1 << 31)
         for attempt in range(3):
+            if first is not None:
+                cand_row, cand_col, n_cand = first
+                first = None
+                break
             cand_row = _empty(cap, t.int32, dev)
             cand_col = _empty(cap, t.int32, dev)
-            if _timed(stats):
-                ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-                ev0.record()
-            launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap)
-            if _timed(stats):
-                ev1.record()
-                stats.setdefault("candidate_events", []).append((ev0, ev1))
-            head = counters[:4].cpu().numpy()
-            n_cand = int(head[0])
-            if use_tiles and stats is not None:
-                stats["pairs_walked"] = stats.get("pairs_walked", 0) + int(head[2])
-                stats["postings_walked"] = stats.get("postings_walked", 0) + int(head[3])
+            n_cand = timed_launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap)
             if n_cand <= cap:
                 break
             if n_cand * 24 > 96 * 2**30:
@@ -948,6 +991,7 @@ def tfidf_sorted(data, offsets, n_master, ngram, flags, dtype, device=None, stat
     master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
     master.nnz_parent = nnz
     if n_master == n_docs:
+        master._df = df[:max(V, 1)]       # fitted on exactly these rows: the vectoriser's df is sg_feature_df(master)
         return master, None, vocab
     dup = DeviceCSR((n_docs - n_master, V), indptr[n_master:], indices, val, val32, nnz - split, np_dtype, 1.0,
                     base=split)
@@ -1023,6 +1067,11 @@ def tfidf_resident(d_bytes, d_off, n_docs, total, n_master, ngram, flags, dtype,
     master = DeviceCSR((n_master, V), indptr[:n_master + 1], indices, val, val32, split, np_dtype, 1.0, base=0)
     master.nnz_parent = nnz
     if n_master == n_docs:
+        if df_allreduce is None and n_docs_fit is None:
+            # fitted on exactly these rows: the vectoriser's df, in column order, is sg_feature_df(master)
+            col_df = _empty(max(V, 1), t.int32, device)
+            _lib.check(L.sg_tfidf_vocab_df(_ptr(df), _ptr(rank), int(ngram), _ptr(col_df), _stream()))
+            master._df = col_df
         return master, None, vocab
     dup = DeviceCSR((n_docs - n_master, V), indptr[n_master:], indices, val, val32, nnz - split, np_dtype, 1.0,
                     base=split)

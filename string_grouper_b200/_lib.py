@@ -42,6 +42,7 @@ SIGNATURES = {
     "sg_tfidf_finalize_workspace_bytes": (_sz, [_i64, _i32]),
     "sg_tfidf_finalize": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sg_tfidf_vocab_keys": (_i32, [_p, _p, _i32, _p, _p]),
+    "sg_tfidf_vocab_df": (_i32, [_p, _p, _i32, _p, _p]),
     "sg_tfidf64_count": (_i32, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "sg_tfidf64_finalize_workspace_bytes": (_sz, [_i64, _i64]),
     "sg_tfidf64_finalize": (_i32, [_p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
@@ -68,7 +69,7 @@ SIGNATURES = {
     "sg_tiles_candidates": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _p, _p, _i32, _p, _p, _i64,
                                    _p, _p, _p, _i32, _p]),
     "sg_order_workspace_bytes": (_sz, [_i64, _i64]),
-    "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _i32, _p, _p, _sz, _p]),
+    "sg_heavy_features": (_i32, [_i64, _i64, _p, _p, _p, _i32, _p, _p, _sz, _p]),
     "sg_row_order": (_i32, [_i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _sz, _p]),
     "sg_rescore": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _p, _p, _i64, _p]),
     "sg_topn_rows_cap": (_i32, []),

@@ -94,9 +94,9 @@ size_t sg_order_workspace_bytes(int64_t n_rows, int64_t n_cols) {
 }
 
 // hrank[n_cols] (int8): rank of each feature among the `n_heavy` (<= 64) most frequent features of the
-// matrix (indptr, indices) with n_rows rows, -1 for the others.
-int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices, int n_heavy,
-                      int8_t *hrank, void *ws, size_t ws_bytes, void *stream_) {
+// matrix (indptr, indices) with n_rows rows, -1 for the others.  df_in (optional): its document frequencies.
+int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, const int32_t *indices,
+                      const int32_t *df_in, int n_heavy, int8_t *hrank, void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n_heavy < 0 || n_heavy > 64) return fail(SG_ERR_INVALID, "n_heavy must be in [0, 64]");
     if (n_cols <= 0) return SG_OK;
@@ -110,14 +110,17 @@ int sg_heavy_features(int64_t n_rows, int64_t n_cols, const int64_t *indptr, con
     cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, df, df_sorted, cols, cols_sorted, n_cols);
     char *tmp = ar.take<char>(b1);
     if (!ar.ok()) return fail(SG_ERR_INVALID, "order workspace too small (%zu < %zu)", ws_bytes, ar.off);
-    SG_CUDA_TRY(cudaMemsetAsync(df, 0, (size_t)n_cols * 4, st));
-    if (n_rows > 0) {
-        order_df_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, df);
-        SG_LAUNCH_CHECK();
+    if (!df_in) {      // no document frequencies at hand (sg_feature_df / the vectoriser's own): count them here
+        SG_CUDA_TRY(cudaMemsetAsync(df, 0, (size_t)n_cols * 4, st));
+        if (n_rows > 0) {
+            order_df_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(n_rows, indptr, indices, df);
+            SG_LAUNCH_CHECK();
+        }
+        df_in = df;
     }
     order_iota_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(n_cols, cols);
     SG_LAUNCH_CHECK();
-    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, b1, df, df_sorted, cols, cols_sorted, n_cols, 0, 32, st));
+    SG_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, b1, df_in, df_sorted, cols, cols_sorted, n_cols, 0, 32, st));
     order_hrank_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(n_cols, cols_sorted, n_heavy, hrank);
     SG_LAUNCH_CHECK();
     if (n_heavy > 0) {

@@ -213,6 +213,12 @@ __global__ void vocab_keys_kernel(int64_t slots, const int32_t *__restrict__ df,
     if (i < slots && df[i] > 0) keys_out[rank[i]] = (uint32_t)i;
 }
 
+__global__ void vocab_df_kernel(int64_t slots, const int32_t *__restrict__ df, const int32_t *__restrict__ rank,
+                                int32_t *__restrict__ df_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < slots && df[i] > 0) df_out[rank[i]] = df[i];
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -308,6 +314,15 @@ int sg_tfidf_vocab_keys(const int32_t *df_table, const int32_t *rank_table, int 
     const int64_t slots = sg_tfidf_table_slots(ngram);
     if (slots < 0) return fail(SG_ERR_UNSUPPORTED, "ngram_size %d unsupported (1..4)", ngram);
     vocab_keys_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(slots, df_table, rank_table, keys_out);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+int sg_tfidf_vocab_df(const int32_t *df_table, const int32_t *rank_table, int ngram, int32_t *df_out, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int64_t slots = sg_tfidf_table_slots(ngram);
+    if (slots < 0) return fail(SG_ERR_UNSUPPORTED, "ngram_size %d unsupported (1..4)", ngram);
+    vocab_df_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(slots, df_table, rank_table, df_out);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }

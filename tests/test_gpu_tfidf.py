@@ -209,3 +209,31 @@ def test_degenerate_inputs():
     # groups on a tiny input
     g = api.group_similar_strings(pd.Series(["foo inc", "foo inc.", "bar"]))
     assert g["group_rep_index"].tolist() == [0, 0, 2]
+
+
+@pytest.mark.parametrize("kw", [{}, {"ngram_size": 2}, {"ngram_size": 5}, {"normalize_to_ascii": False}])
+def test_vectoriser_df_is_the_feature_df_of_the_matrix(kw):
+    """Self-match: the matrix holds exactly the fitted rows, so K1 hands its document frequencies (column order)
+    to K2 instead of a second count (sg_feature_df); with two Series nothing is handed over."""
+    import ctypes
+    from string_grouper_b200 import _device as D, _lib
+    texts = make_names(3000, seed=5) + EDGE
+    _, m, _ = _device_matrices(texts, **kw)
+    assert m._df is not None
+    handed = m._df.cpu().numpy()[:m.shape[1]].copy()
+    m._df = None
+    counted = D.feature_df(m).cpu().numpy()
+    ref = np.bincount(m.to_scipy().indices, minlength=m.shape[1])
+    assert np.array_equal(counted, ref) and np.array_equal(handed, ref)
+    # the heavy-feature ranks are the same whether sg_heavy_features counts or is given the frequencies
+    t, L = D.torch(), _lib.load()
+    ws_bytes = int(L.sg_order_workspace_bytes(m.shape[0], m.shape[1]))
+    ws = t.empty(ws_bytes, dtype=t.uint8, device=m.device)
+    own = t.empty(m.shape[1], dtype=t.int8, device=m.device)
+    _lib.check(L.sg_heavy_features(m.shape[0], m.shape[1], ctypes.c_void_p(m.d_indptr.data_ptr()),
+                                   ctypes.c_void_p(m.d_indices.data_ptr()), None, 64,
+                                   ctypes.c_void_p(own.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes, D._stream()))
+    t.cuda.synchronize()
+    assert np.array_equal(own.cpu().numpy(), D.heavy_features(m).cpu().numpy())
+    _, master, dup = _device_matrices(texts[:2000], texts[2000:], **kw)
+    assert master._df is None and dup._df is None
