@@ -190,10 +190,14 @@ int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[d
                   float budget, float threshold, float margin, float margin_per_feature,
                   int32_t *out_indices /*[dev]*/, float *out_val32 /*[dev]*/, int32_t *out_len /*[dev] per row id*/,
                   float *out_threshold /*[dev] per row id*/, float *out_pruned_norm /*[dev] per row id*/,
+                  void *out_group_norms /*[dev] fp16[8] per row id (16-byte aligned) or NULL: |x_P| per group of 8
+                                          heavy ranks, rounded up; needs `prunable` = sg_heavy_features ranks*/,
                   void *stream);
 int sg_heavy_norms(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[dev]*/,
                    const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/, const int8_t *hrank /*[dev]*/,
-                   float *out_norm /*[dev] row_end-row_begin*/, void *stream);
+                   float *out_norm /*[dev] row_end-row_begin*/,
+                   void *out_group_norms /*[dev] fp16[8] per row of the range or NULL: |y_H| per group, rounded up*/,
+                   void *stream);
 int sg_tile_bounds(int64_t n_right, const int32_t *perm /*[dev] position -> row, or NULL*/,
                    const float *row_norm /*[dev] per row*/, int tile_w, float *bound /*[dev] n_tiles*/, void *stream);
 
@@ -228,7 +232,10 @@ int sg_cossim_candidates(const int64_t *a_indptr /*[dev]*/, const int32_t *a_len
                          const float *pruned_norm_row /*[dev] per row id, or NULL*/,
                          const float *tile_bound /*[dev] sg_num_tiles_padded() entries, zero padded*/,
                          int64_t tiles_per_group, int32_t *cand_row /*[dev] cap*/,
-                         int32_t *cand_col /*[dev] cap*/, int64_t cand_cap,
+                         int32_t *cand_col /*[dev] cap*/,
+                         float *cand_partial /*[dev] cap or NULL: the candidate's partial score over the kept features
+                                               as accumulated (input of sg_rescore_refined)*/,
+                         int64_t cand_cap,
                          unsigned long long *cand_count /*[dev] 1*/,
                          unsigned long long *row_queue /*[dev] 1*/, int warps_per_cta, void *stream);
 
@@ -300,6 +307,23 @@ int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
                int32_t *keep_col /*[dev] n_cand or NULL*/, unsigned long long *keep_count /*[dev] 1 or NULL*/,
                int32_t *row_cnt /*[dev] per left row - row_begin, zeroed by the caller, or NULL: += kept per row*/,
                int64_t row_begin, void *stream);
+/* sg_rescore behind the per-candidate grouped bound of csrc/sg_prune.cu: candidate i = (r, c) is only scored when
+ *   cand_partial[i] + sum_g left_group_norms[r][g] * right_group_norms[c][g]  >  row_threshold[r]
+ * (partial score from sg_cossim_candidates, group norms from sg_prune_rows / sg_heavy_norms, row_threshold =
+ * sg_prune_rows' out_threshold): the others cannot reach the threshold and their right rows are never read.  Same
+ * kept set and scores as sg_rescore on the same candidates.  *refined_count [dev] (zeroed, or NULL) += candidates that
+ * were scored.  keep_count / keep_row / keep_col are required. */
+int sg_rescore_refined(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
+                       const float *cand_partial /*[dev] n_cand*/,
+                       const void *left_group_norms /*[dev] fp16[8] per left row id*/,
+                       const void *right_group_norms /*[dev] fp16[8] per right row id*/,
+                       const float *row_threshold /*[dev] per left row id*/,
+                       const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
+                       const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
+                       double *score_out /*[dev] n_cand*/, double keep_threshold, int32_t *keep_row /*[dev] n_cand*/,
+                       int32_t *keep_col /*[dev] n_cand*/, unsigned long long *keep_count /*[dev] 1*/,
+                       unsigned long long *refined_count /*[dev] 1 or NULL*/,
+                       int32_t *row_cnt /*[dev] or NULL*/, int64_t row_begin, void *stream);
 
 /*
  * Per-row selection: keep score > threshold (strict, sg.py:729/:740), at most

@@ -33,6 +33,7 @@ MAX_BUCKETS = int(os.environ.get("SG_B200_MAX_BUCKETS", str(400_000_000)))      
 CAND_CHUNK = int(os.environ.get("SG_B200_CAND_CHUNK", str(1 << 28)))            # candidates per chunk of left rows
 # up to this many (left row, right row) pairs the candidates kernel is launched without a sizing pass (see cossim_topn)
 OPTIMISTIC_PAIRS = float(os.environ.get("SG_B200_OPTIMISTIC_PAIRS", "5e11"))
+REFINE = os.environ.get("SG_B200_REFINE", "1") != "0"      # grouped per-candidate bound before the exact re-score
 # K2 formulation: "row" (the default) = one warp per left row over L2-resident posting buckets (csrc/sg_cossim.cu; also
 # the general path: negative values, norms above 1, near-zero thresholds); "tiles" = right tiles staged through TMA into
 # shared memory (csrc/sg_tiles.cu), for L2-normalised non-negative operands.  Measured on B200 at 663k rows the row kernel
@@ -143,6 +144,7 @@ class DeviceCSR:
         self.global_rows = None
         self._df = None             # document frequency of every feature (sg_feature_df)
         self._heavy_norm = None     # per-row norm over the heavy features (sg_heavy_norms)
+        self._heavy_groups = None   # the same per group of 8 heavy ranks, fp16 (sg_rescore_refined)
         self.nonneg = True          # no negative stored value (K1 output; checked for uploaded matrices)
 
     @property
@@ -230,16 +232,19 @@ def heavy_features(B):
     return hrank
 
 
-def heavy_norms(M, hrank, row_begin=0, row_end=None):
-    """fp32 norm of rows [row_begin,row_end) of M over the heavy features, rounded up (sg_heavy_norms)."""
+def heavy_norms(M, hrank, row_begin=0, row_end=None, groups=False):
+    """fp32 norm of rows [row_begin,row_end) of M over the heavy features, rounded up (sg_heavy_norms); with
+    `groups` also the fp16 norms per group of 8 heavy ranks (8 per row): (norm, group_norms)."""
     t = require_cuda()
     L = _lib.load()
     row_end = M.shape[0] if row_end is None else row_end
-    out = _empty(max(row_end - row_begin, 0), t.float32, M.device)
+    n = max(row_end - row_begin, 0)
+    out = _empty(n, t.float32, M.device)
+    grp = _empty(8 * n, t.float16, M.device) if groups else None
     _lib.check(L.sg_heavy_norms(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(M.d_val32),
-                                _ptr(hrank), _ptr(out), _stream()))
+                                _ptr(hrank), _ptr(out), _ptr(grp), _stream()))
     LAUNCH_COUNTS["prune"] += 1
-    return out
+    return (out, grp) if groups else out
 
 
 def row_order(M, hrank, row_begin=0, row_end=None, want_rank=True, row_norm=None, norm_scale=1.0):
@@ -262,7 +267,7 @@ def right_order(B):
     """(hrank, perm, rank) of the right matrix: heavy features, rows sorted by (quantised heavy norm, signature)."""
     if B._order is None:
         hrank = heavy_features(B)
-        B._heavy_norm = heavy_norms(B, hrank)
+        B._heavy_norm, B._heavy_groups = heavy_norms(B, hrank, groups=True)
         perm, rank = row_order(B, hrank, row_norm=B._heavy_norm, norm_scale=1.0 / max(B.norm_bound, 1e-30))
         B._order = (hrank, perm, rank)
     return B._order
@@ -428,8 +433,8 @@ def feature_df(B):
 
 def prune_left(A, B, hrank, row_begin, row_end, threshold, margin, margin_per_feature, frac):
     """Exact threshold pruning of rows [row_begin,row_end) of A against B (sg_prune_rows); only B's heavy
-    features (hrank >= 0) are prunable.  Returns (indices, val32, row_len, row_threshold, pruned_norm) device
-    arrays indexed like A's own."""
+    features (hrank >= 0) are prunable.  Returns (indices, val32, row_len, row_threshold, pruned_norm,
+    pruned_group_norms) device arrays indexed like A's own."""
     t = require_cuda()
     L = _lib.load()
     df = feature_df(B)
@@ -438,14 +443,15 @@ def prune_left(A, B, hrank, row_begin, row_end, threshold, margin, margin_per_fe
     p_len = _empty(A.shape[0], t.int32, A.device)
     p_thr = _empty(A.shape[0], t.float32, A.device)
     p_xp = _empty(A.shape[0], t.float32, A.device)
+    p_xg = _empty(8 * A.shape[0], t.float16, A.device)      # |x_P| per group of 8 heavy ranks
     budget = max(float(frac) * (float(threshold) - margin), 0.0)
     # the kernel works on left weights as stored and right rows of norm <= B.norm_bound
     _lib.check(L.sg_prune_rows(row_begin, row_end, _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), _ptr(df),
                                _ptr(hrank), float(B.norm_bound), budget, float(threshold), float(margin),
                                float(margin_per_feature), _ptr(p_idx), _ptr(p_val), _ptr(p_len), _ptr(p_thr),
-                               _ptr(p_xp), _stream()))
+                               _ptr(p_xp), _ptr(p_xg), _stream()))
     LAUNCH_COUNTS["prune"] += 1
-    return p_idx, p_val, p_len, p_thr, p_xp
+    return p_idx, p_val, p_len, p_thr, p_xp, p_xg
 
 
 def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, warps=None, stats=None,
@@ -538,7 +544,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
 
     def launch_tiles(perm, n, row_buf, col_buf, capacity):
         """pack the pruned rows of `perm`, block-max filter -> survivor bits, tile kernel"""
-        l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+        l_idx, l_val, l_len, l_thr, l_xp, _ = pruned["arrays"]
         stride = (n + 31) // 32 * 32
         rowinfo = _empty(4 * stride, t.int32, dev)
         mask = _empty(mask_words * stride, t.int32, dev)
@@ -554,17 +560,17 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
                                          _ptr(col_buf), capacity, c_count, c_queue, c_walk, warps, _stream()))
         LAUNCH_COUNTS["tiles"] += 3
 
-    def launch(perm, rb, re_, row_buf, col_buf, capacity):
+    def launch(perm, rb, re_, row_buf, col_buf, capacity, partial_buf=None):
         if use_tiles:
             return launch_tiles(perm, re_ - rb, row_buf, col_buf, capacity)
-        l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+        l_idx, l_val, l_len, l_thr, l_xp, _ = pruned["arrays"]
         counters.zero_()
         _lib.check(L.sg_cossim_candidates(
             _ptr(A.d_indptr), _ptr(l_len), _ptr(l_idx), _ptr(l_val), rb, re_, _ptr(perm), n_right,
             A.shape[1], _ptr(bucket_dir), _ptr(bucket_maxw), _ptr(post), _ptr(perm_b), tile_w, acc_code,
             max(B.norm_bound, 1.0),
-            thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf), capacity,
-            c_count, c_queue, warps, _stream()))
+            thr_c, _ptr(l_thr), _ptr(l_xp), _ptr(tile_bound), tiles_per_group, _ptr(row_buf), _ptr(col_buf),
+            _ptr(partial_buf), capacity, c_count, c_queue, warps, _stream()))
         LAUNCH_COUNTS["candidates"] += 1
 
     # Exact threshold pruning of the left rows (the fixed-point tile always takes per-row thresholds: its margin
@@ -581,13 +587,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             pruned["arrays"] = prune_left(A, B, hrank, row_begin, row_end, float(threshold), margin, margin_pf,
                                           level if thr_c > 0.0 else 0.0)
         else:
-            pruned["arrays"] = (A.d_indices, A.d_val32, None, None, None)
+            pruned["arrays"] = (A.d_indices, A.d_val32, None, None, None, None)
 
-    def timed_launch(perm, rb, re_, row_buf, col_buf, capacity):
+    def timed_launch(perm, rb, re_, row_buf, col_buf, capacity, partial_buf=None):
         if _timed(stats):
             ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             ev0.record()
-        launch(perm, rb, re_, row_buf, col_buf, capacity)
+        launch(perm, rb, re_, row_buf, col_buf, capacity, partial_buf)
         if _timed(stats):
             ev1.record()
             stats.setdefault("candidate_events", []).append((ev0, ev1))
@@ -610,21 +616,25 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
     # shard).  While a wasted launch costs no more than a few tens of ms, launch everything at once at the first
     # level into buffers of the density limit; only an overflow or a count above the limit falls back to the
     # sample / level search / row chunks below, and then the exact count of the first level is already known.
+    # Candidates of the fixed-point row kernel carry their partial score: sg_rescore_refined re-tests each with the
+    # grouped bound (csrc/sg_prune.cu) before its right row is read.
+    refine = REFINE and not use_tiles and acc == "u16" and margin_pf > 0.0
     if not fixed_cap and float(n_rows) * float(n_right) <= OPTIMISTIC_PAIRS:
         prune = levels[0]
         prepare(prune)
         cap0 = int(min(int(dense) + (1 << 22), CAND_CHUNK))
         cand_row0 = _empty(cap0, t.int32, dev)
         cand_col0 = _empty(cap0, t.int32, dev)
+        cand_part0 = _empty(cap0, t.float32, dev) if refine else None
         mark(stats, "prune_sample")
-        n0 = timed_launch(perm_a, row_begin, row_end, cand_row0, cand_col0, cap0)
+        n0 = timed_launch(perm_a, row_begin, row_end, cand_row0, cand_col0, cap0, cand_part0)
         mark(stats, "candidates")
         too_dense = len(levels) > 1 and sample is not None and n0 > dense
         if n0 <= cap0 and not too_dense:
-            first = (cand_row0, cand_col0, n0)
+            first = (cand_row0, cand_col0, cand_part0, n0)
             search = False
         else:
-            del cand_row0, cand_col0
+            del cand_row0, cand_col0, cand_part0
             if _timed(stats):
                 stats["wasted_launch"] = True
             if too_dense:
@@ -641,7 +651,7 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             est = int(counters[0].item()) * stride
             if est <= dense:
                 break
-    l_idx, l_val, l_len, l_thr, l_xp = pruned["arrays"]
+    l_idx, l_val, l_len, l_thr, l_xp, l_xg = pruned["arrays"]
     mark(stats, "prune_sample")
     if stats is not None:
         stats["prune"], stats["acc"] = prune, acc
@@ -672,12 +682,13 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
             cap = min(max(int(1.3 * est * (hi - lo) / n_rows) + (1 << 22), 1 << 22), 1 << 31)
         for attempt in range(3):
             if first is not None:
-                cand_row, cand_col, n_cand = first
+                cand_row, cand_col, cand_part, n_cand = first
                 first = None
                 break
             cand_row = _empty(cap, t.int32, dev)
             cand_col = _empty(cap, t.int32, dev)
-            n_cand = timed_launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap)
+            cand_part = _empty(cap, t.float32, dev) if refine else None
+            n_cand = timed_launch(perm_chunk, row_begin, row_begin + (hi - lo), cand_row, cand_col, cap, cand_part)
             if n_cand <= cap:
                 break
             if n_cand * 24 > 96 * 2**30:
@@ -693,20 +704,29 @@ def cossim_topn(A, B, top_n, threshold, row_begin=0, row_end=None, tile_w=None, 
         keep_row = _empty(n_cand, t.int32, dev)
         keep_col = _empty(n_cand, t.int32, dev)
         counters.zero_()
-        _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
-                                _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt, _ptr(score),
-                                float(threshold), _ptr(keep_row), _ptr(keep_col), c_count, _ptr(row_cnt), row_begin,
-                                _stream()))
+        if refine and cand_part is not None and l_xg is not None:
+            _lib.check(L.sg_rescore_refined(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(cand_part), _ptr(l_xg),
+                                            _ptr(B._heavy_groups), _ptr(l_thr), _ptr(A.d_indptr), _ptr(A.d_indices),
+                                            _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt,
+                                            _ptr(score), float(threshold), _ptr(keep_row), _ptr(keep_col), c_count,
+                                            c_walk, _ptr(row_cnt), row_begin, _stream()))
+        else:
+            _lib.check(L.sg_rescore(n_cand, _ptr(cand_row), _ptr(cand_col), _ptr(A.d_indptr), _ptr(A.d_indices),
+                                    _ptr(A.d_val), _ptr(B.d_indptr), _ptr(B.d_indices), _ptr(B.d_val), dt,
+                                    _ptr(score), float(threshold), _ptr(keep_row), _ptr(keep_col), c_count,
+                                    _ptr(row_cnt), row_begin, _stream()))
         LAUNCH_COUNTS["rescore"] += 1
         if lo + rows_per_chunk >= n_rows:      # last chunk: the largest row rides along with the read-back
             _lib.check(L.sg_row_count_max(n_rows, _ptr(row_cnt), c_queue, _stream()))      # counters[1], zeroed above
-        head = counters[:2].cpu().numpy()
+        head = counters[:3].cpu().numpy()
         n_keep, max_row_cnt = int(head[0]), int(head[1])
+        if refine and stats is not None:
+            stats["n_refined"] = stats.get("n_refined", 0) + int(head[2])
         mark(stats, "rescore")
         if n_chunks > 1:      # release the chunk-sized buffers, keep the survivors
             keep_row, keep_col, score = keep_row[:n_keep].clone(), keep_col[:n_keep].clone(), score[:n_keep].clone()
         kept.append((keep_row, keep_col, score, n_keep))
-        del cand_row, cand_col
+        del cand_row, cand_col, cand_part
     if len(kept) == 1:
         cand_row, cand_col, score, n_cand = kept[0]
     else:

@@ -125,6 +125,10 @@ struct AccOps<float> {
         return (__uint_as_float(v.x) > thr ? 1u : 0u) | (__uint_as_float(v.y) > thr ? 2u : 0u) |
                (__uint_as_float(v.z) > thr ? 4u : 0u) | (__uint_as_float(v.w) > thr ? 8u : 0u);
     }
+    // element i of the vector as a score
+    static __device__ __forceinline__ float value(const uint4 &v, int i) {
+        return __uint_as_float(i < 2 ? (i == 0 ? v.x : v.y) : (i == 2 ? v.z : v.w));
+    }
 };
 template <>
 struct AccOps<uint16_t> {
@@ -149,6 +153,10 @@ struct AccOps<uint16_t> {
     static __device__ __forceinline__ unsigned above(const uint4 &v, int thr) {
         return pair_above(v.x, thr) | (pair_above(v.y, thr) << 2) | (pair_above(v.z, thr) << 4) |
                (pair_above(v.w, thr) << 6);
+    }
+    static __device__ __forceinline__ float value(const uint4 &v, int i) {
+        const unsigned w = i < 4 ? (i < 2 ? v.x : v.y) : (i < 6 ? v.z : v.w);
+        return (float)((w >> ((i & 1) << 4)) & 0xffffu) * (1.f / FIX_ONE);
     }
 };
 
@@ -244,7 +252,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                          int64_t T, int64_t tiles_per_group, float a_scale, float thr_all,
                          const float *__restrict__ thr_row, const float *__restrict__ xp_norm,
                          const float *__restrict__ tile_bound, int32_t *__restrict__ cand_row,
-                         int32_t *__restrict__ cand_col, unsigned long long cap,
+                         int32_t *__restrict__ cand_col, float *__restrict__ cand_partial, unsigned long long cap,
                          unsigned long long *__restrict__ cand_count, unsigned long long *__restrict__ row_queue) {
     typedef AccOps<AccT> Ops;
     typedef typename Ops::val_t val_t;
@@ -370,8 +378,9 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                     for (int c0 = 0; c0 < n16; c0 += 32) {
                         const int c = c0 + lane;
                         unsigned m = 0;
+                        uint4 v = zero4;
                         if (c < n16) {
-                            const uint4 v = acc16[c];
+                            v = acc16[c];
                             if (v.x | v.y | v.z | v.w) {
                                 acc16[c] = zero4;
                                 m = Ops::above(v, thr_c);
@@ -395,6 +404,7 @@ cossim_candidates_kernel(const int64_t *__restrict__ a_indptr, const int32_t *__
                                     const int col = t * W + c * Ops::PER16 + i;
                                     cand_row[slot] = (int32_t)row;
                                     cand_col[slot] = perm_b ? perm_b[col] : col;
+                                    if (cand_partial) cand_partial[slot] = Ops::value(v, i);
                                 }
                                 ++slot;
                             }
@@ -451,12 +461,48 @@ __device__ __forceinline__ T merge_dot(const int32_t *__restrict__ ai, const T *
     return sum;
 }
 
+// Same sum, same order, fewer L1 wavefronts: the right row's indices are the scattered loads of this kernel (every
+// lane its own row), so they come four at a time as aligned 16-byte vectors (elements of the neighbouring row in the
+// first vector are skipped; the last, partial vector is read by scalar loads so nothing beyond the row is touched).
+// The left row is shared by most lanes of a warp (candidates arrive grouped by row): its loads are broadcasts.
+template <typename T>
+__device__ __forceinline__ T merge_dot_vec(const int32_t *__restrict__ ai, const T *__restrict__ av, int64_t pa,
+                                           int64_t ea, const int32_t *__restrict__ bi,
+                                           const T *__restrict__ bv, int64_t pb, int64_t eb) {
+    T sum = (T)0;
+    if (pa >= ea || pb >= eb) return sum;
+    const int32_t END = 0x7fffffff;
+    int32_t fa = ai[pa];
+    for (int64_t k = pb & ~(int64_t)3; k < eb; k += 4) {
+        int32_t f[4];
+        if (k + 4 <= eb) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(bi + k));
+            f[0] = q.x, f[1] = q.y, f[2] = q.z, f[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = k + j < eb ? bi[k + j] : END;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t p = k + j;
+            if (p < pb || p >= eb) continue;
+            const int32_t fb = f[j];
+            while (fa < fb) {
+                if (++pa >= ea) return sum;
+                fa = ai[pa];
+            }
+            if (fa == fb) sum = ExactOps<T>::add(sum, ExactOps<T>::mul(av[pa], bv[p]));
+        }
+    }
+    return sum;
+}
+
 // `keep_count` == NULL: out[i] = exact score of candidate i.  Otherwise only the candidates whose exact score
 // exceeds `keep_thr` (strict, string_grouper.py:729/:740) survive, appended in no particular order to
 // (keep_row, keep_col, out) through one warp-aggregated atomic per warp: the selection sorts that follow then
 // work on the matches-to-be instead of on every candidate the pruned traversal had to report.
-template <typename T>
-__global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 8) rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
                                const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
                                const T *__restrict__ a_val, const int64_t *__restrict__ b_indptr,
                                const int32_t *__restrict__ b_idx, const T *__restrict__ b_val,
@@ -470,8 +516,10 @@ __global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const 
     if (i < n) {
         r = cr[i];
         c = cc[i];
-        sc = (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
-                                  b_indptr[c + 1]);
+        sc = VEC ? (double)merge_dot_vec<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+                                            b_indptr[c + 1])
+                 : (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+                                        b_indptr[c + 1]);
         if (!keep_count) out[i] = sc;
         keep = keep_count && sc > keep_thr;
     }
@@ -489,6 +537,89 @@ __global__ void rescore_kernel(int64_t n, const int32_t *__restrict__ cr, const 
         out[w] = sc;
         if (row_cnt) atomicAdd(row_cnt + (r - row_begin), 1);       // survivors per row: sizes the row buckets of
                                                                     // sg_topn_select_rows
+    }
+}
+
+// sg_rescore_refined: a CTA takes REFINE_CHUNK consecutive candidates.  Pass 1 re-tests each with the grouped bound
+// (one 16-byte load of the column's group norms, the row's are shared by neighbours) and compacts the survivors'
+// positions into shared memory; pass 2 scores the survivors with full warps, exactly as rescore_kernel does.
+constexpr int REFINE_CHUNK = 2048;
+
+__device__ __forceinline__ float group_dot(const uint4 &x, const uint4 &y) {
+    const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
+    const __half2 *yh = reinterpret_cast<const __half2 *>(&y);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(xh[k]), b = __half22float2(yh[k]);
+        d = fmaf(a.x, b.x, d);          // products of two fp16 values are exact in fp32
+        d = fmaf(a.y, b.y, d);
+    }
+    return d * (1.f + 1e-5f) + 1e-6f;   // the eight fp32 additions, rounded up
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 8)
+rescore_refined_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t *__restrict__ cc,
+                       const float *__restrict__ partial, const uint4 *__restrict__ xg,
+                       const uint4 *__restrict__ yg, const float *__restrict__ thr_row,
+                       const int64_t *__restrict__ a_indptr, const int32_t *__restrict__ a_idx,
+                       const T *__restrict__ a_val, const int64_t *__restrict__ b_indptr,
+                       const int32_t *__restrict__ b_idx, const T *__restrict__ b_val, double *__restrict__ out,
+                       double keep_thr, int32_t *__restrict__ keep_row, int32_t *__restrict__ keep_col,
+                       unsigned long long *__restrict__ keep_count, unsigned long long *__restrict__ refined_count,
+                       int32_t *__restrict__ row_cnt, int64_t row_begin) {
+    __shared__ uint16_t live[REFINE_CHUNK];
+    __shared__ int n_live;
+    const int lane = threadIdx.x & 31;
+    const int64_t base = (int64_t)blockIdx.x * REFINE_CHUNK;
+    if (threadIdx.x == 0) n_live = 0;
+    __syncthreads();
+    for (int o = threadIdx.x; o < REFINE_CHUNK; o += 256) {          // uniform trip count: the ballots need every lane
+        const int64_t i = base + o;
+        bool pass = false;
+        if (i < n) {
+            const int32_t r = cr[i], c = cc[i];
+            pass = partial[i] + group_dot(xg[r], __ldg(yg + c)) > thr_row[r];
+        }
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (m) {
+            int w = 0;
+            if (lane == 0) w = atomicAdd(&n_live, __popc(m));
+            w = __shfl_sync(FULL, w, 0);
+            if (pass) live[w + __popc(m & ((1u << lane) - 1u))] = (uint16_t)o;
+        }
+    }
+    __syncthreads();
+    const int total = n_live;
+    if (refined_count && threadIdx.x == 0 && total) atomicAdd(refined_count, (unsigned long long)total);
+    for (int j0 = 0; j0 < total; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        int32_t r = 0, c = 0;
+        double sc = 0.0;
+        bool keep = false;
+        if (j < total) {
+            const int64_t i = base + live[j];
+            r = cr[i];
+            c = cc[i];
+            sc = VEC ? (double)merge_dot_vec<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+                                                b_indptr[c + 1])
+                     : (double)merge_dot<T>(a_idx, a_val, a_indptr[r], a_indptr[r + 1], b_idx, b_val, b_indptr[c],
+                                            b_indptr[c + 1]);
+            keep = sc > keep_thr;
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (!m) continue;
+        unsigned long long w0 = 0;
+        if (lane == __ffs(m) - 1) w0 = atomicAdd(keep_count, (unsigned long long)__popc(m));
+        w0 = __shfl_sync(FULL, w0, __ffs(m) - 1);
+        if (keep) {
+            const unsigned long long w = w0 + __popc(m & ((1u << lane) - 1u));
+            keep_row[w] = r;
+            keep_col[w] = c;
+            out[w] = sc;
+            if (row_cnt) atomicAdd(row_cnt + (r - row_begin), 1);
+        }
     }
 }
 
@@ -692,7 +823,7 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
                              const void *postings, const int32_t *perm_b, int tile_w, int64_t tiles_per_group,
                              float a_scale,
                              float thr_c, const float *thr_row, const float *xp_norm, const float *tile_bound,
-                             int32_t *cand_row, int32_t *cand_col,
+                             int32_t *cand_row, int32_t *cand_col, float *cand_partial,
                              int64_t cand_cap, unsigned long long *cand_count, unsigned long long *row_queue,
                              int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)NW * tile_w * sizeof(AccT);
@@ -711,8 +842,8 @@ static int launch_candidates(const int64_t *a_indptr, const int32_t *a_len, cons
         a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, (const int2 *)bucket_dir,
         (const uint32_t *)bucket_maxw, (const uint32_t *)postings, perm_b, (int)sg_num_tiles_padded(n_right, tile_w),
         tile_w, T, tiles_per_group,
-        a_scale, thr_c, thr_row, xp_norm, tile_bound, cand_row, cand_col, (unsigned long long)cand_cap, cand_count,
-        row_queue);
+        a_scale, thr_c, thr_row, xp_norm, tile_bound, cand_row, cand_col, cand_partial, (unsigned long long)cand_cap,
+        cand_count, row_queue);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }
@@ -726,7 +857,7 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
                          float cand_threshold,
                          const float *cand_threshold_row, const float *pruned_norm_row, const float *tile_bound,
                          int64_t tiles_per_group, int32_t *cand_row,
-                         int32_t *cand_col, int64_t cand_cap, unsigned long long *cand_count,
+                         int32_t *cand_col, float *cand_partial, int64_t cand_cap, unsigned long long *cand_count,
                          unsigned long long *row_queue, int warps_per_cta, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (row_end <= row_begin || n_right <= 0) return SG_OK;
@@ -750,7 +881,7 @@ int sg_cossim_candidates(const int64_t *a_indptr, const int32_t *a_len, const in
 #define SG_ARGS                                                                                              \
     a_indptr, a_len, a_indices, a_val32, row_begin, row_end, perm_a, n_right, n_cols, bucket_dir, bucket_maxw, \
         postings, perm_b, tile_w, tiles_per_group, a_scale, cand_threshold, cand_threshold_row, pruned_norm_row,      \
-        tile_bound, cand_row, cand_col, cand_cap, cand_count, row_queue, n_sm, st
+        tile_bound, cand_row, cand_col, cand_partial, cand_cap, cand_count, row_queue, n_sm, st
 #define SG_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
         return acc_dtype == SG_ACC_U16 ? launch_candidates<NW, uint16_t>(SG_ARGS)                           \
@@ -777,18 +908,56 @@ int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
     if (keep_count && (!keep_row || !keep_col)) return fail(SG_ERR_INVALID, "keep_count needs keep_row and keep_col");
     if (row_cnt && !keep_count) return fail(SG_ERR_INVALID, "row_cnt needs keep_count");
     const unsigned grid = (unsigned)((n_cand + 255) / 256);
-    if (dtype == SG_DTYPE_F64)
-        rescore_kernel<double><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
-                                                     (const double *)a_val, b_indptr, b_indices,
-                                                     (const double *)b_val, score_out, keep_threshold, keep_row,
-                                                     keep_col, keep_count, row_cnt, row_begin);
-    else if (dtype == SG_DTYPE_F32)
-        rescore_kernel<float><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices,
-                                                    (const float *)a_val, b_indptr, b_indices,
-                                                    (const float *)b_val, score_out, keep_threshold, keep_row,
-                                                    keep_col, keep_count, row_cnt, row_begin);
-    else
+    const bool vec = ((uintptr_t)b_indices & 15) == 0;      // merge_dot_vec reads aligned 16-byte index vectors
+#define SG_RESCORE(T, VEC)                                                                                        \
+    rescore_kernel<T, VEC><<<grid, 256, 0, st>>>(n_cand, cand_row, cand_col, a_indptr, a_indices, (const T *)a_val, \
+                                                 b_indptr, b_indices, (const T *)b_val, score_out, keep_threshold,  \
+                                                 keep_row, keep_col, keep_count, row_cnt, row_begin)
+    if (dtype == SG_DTYPE_F64) {
+        if (vec) SG_RESCORE(double, 1);
+        else SG_RESCORE(double, 0);
+    } else if (dtype == SG_DTYPE_F32) {
+        if (vec) SG_RESCORE(float, 1);
+        else SG_RESCORE(float, 0);
+    } else {
         return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
+    }
+#undef SG_RESCORE
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+}
+
+int sg_rescore_refined(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col, const float *cand_partial,
+                       const void *left_group_norms, const void *right_group_norms, const float *row_threshold,
+                       const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
+                       const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,
+                       double *score_out, double keep_threshold, int32_t *keep_row, int32_t *keep_col,
+                       unsigned long long *keep_count, unsigned long long *refined_count, int32_t *row_cnt,
+                       int64_t row_begin, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_cand <= 0) return SG_OK;
+    if (!keep_count || !keep_row || !keep_col) return fail(SG_ERR_INVALID, "keep_count, keep_row and keep_col are required");
+    if (!cand_partial || !left_group_norms || !right_group_norms || !row_threshold)
+        return fail(SG_ERR_INVALID, "partial scores, group norms and row thresholds are required");
+    if (((uintptr_t)left_group_norms | (uintptr_t)right_group_norms) & 15)
+        return fail(SG_ERR_INVALID, "group norms must be 16-byte aligned");
+    const unsigned grid = (unsigned)((n_cand + REFINE_CHUNK - 1) / REFINE_CHUNK);
+    const bool vec = ((uintptr_t)b_indices & 15) == 0;
+#define SG_RESCORE(T, VEC)                                                                                         \
+    rescore_refined_kernel<T, VEC><<<grid, 256, 0, st>>>(                                                           \
+        n_cand, cand_row, cand_col, cand_partial, (const uint4 *)left_group_norms, (const uint4 *)right_group_norms, \
+        row_threshold, a_indptr, a_indices, (const T *)a_val, b_indptr, b_indices, (const T *)b_val, score_out,      \
+        keep_threshold, keep_row, keep_col, keep_count, refined_count, row_cnt, row_begin)
+    if (dtype == SG_DTYPE_F64) {
+        if (vec) SG_RESCORE(double, 1);
+        else SG_RESCORE(double, 0);
+    } else if (dtype == SG_DTYPE_F32) {
+        if (vec) SG_RESCORE(float, 1);
+        else SG_RESCORE(float, 0);
+    } else {
+        return fail(SG_ERR_INVALID, "dtype must be SG_DTYPE_F32 or SG_DTYPE_F64");
+    }
+#undef SG_RESCORE
     SG_LAUNCH_CHECK();
     return SG_OK;
 }

@@ -17,9 +17,22 @@
 // below |y| for most rows.  The right rows are ordered by quantised |y_H| first (sg_row_order), so the
 // largest |y_H| inside a column tile (sg_tile_bounds) is close to that of each of its columns and the
 // candidate threshold of (row i, tile t) becomes  threshold - |x_P(i)| * bound(t).
+//
+// Tighter again, per candidate: H is split into SG_HEAVY_GROUPS groups by rank (8 ranks each).  With x_P,g / y_H,g the
+// parts of x_P / y_H in group g,  x_P . y = sum_g x_P,g . y_H,g <= sum_g |x_P,g| |y_H,g|.  sg_prune_rows and
+// sg_heavy_norms store the group norms (fp16, rounded up, 16 bytes per row); sg_rescore_refined re-tests every
+// candidate (row i, column j) with  partial score > threshold(i) - sum_g |x_P,g(i)| |y_H,g(j)|  before it reads the
+// right row: on the 663k benchmark 9 of 10 false candidates of the tile-wide bound go (profiles/r2_notes.md).
+#include <cuda_fp16.h>
+
 #include "sg_common.cuh"
 
 namespace sg {
+
+constexpr int HEAVY_GROUPS = 8;        // 64 heavy ranks / 8
+
+// fp32 norm from a sum of squares, rounded up: relative and absolute slack cover the fp32 arithmetic
+__device__ __forceinline__ float norm_up(float s2) { return s2 > 0.f ? sqrtf(s2) * (1.f + 1e-5f) + 1e-6f : 0.f; }
 
 __global__ void feature_df_kernel(int64_t n_rows, const int64_t *__restrict__ indptr,
                                   const int32_t *__restrict__ indices, int32_t *__restrict__ df) {
@@ -37,7 +50,7 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
                                   float threshold, float margin, float margin_per_feature,
                                   int32_t *__restrict__ out_idx, float *__restrict__ out_val,
                                   int32_t *__restrict__ out_len, float *__restrict__ out_thr,
-                                  float *__restrict__ out_xp) {
+                                  float *__restrict__ out_xp, __half *__restrict__ out_xg) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     const int lane = lane_id();
@@ -49,6 +62,7 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
     const float lim2 = lim * lim;
     int kept = 0;
     float norm_p2 = 0.f;
+    float group_p2 = 0.f;      // lanes 0..7: squared norm of the pruned features of group `lane`
     for (int base = 0; base < nf; base += 32) {
         const int k = base + lane;
         float my_key = -1.f, my_w2 = 0.f, my_v = 0.f;
@@ -91,6 +105,16 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
             out_val[w] = my_v;
         }
         kept += __popc(km);
+        if (out_xg) {          // pruned features are few: one at a time, the lane of its group adds it
+            const int my_g = in_p ? (int)prunable[my_f] >> 3 : 0;
+            unsigned pm = __ballot_sync(FULL, in_p);
+            while (pm) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const float w2 = __shfl_sync(FULL, my_w2, j);
+                if (lane == __shfl_sync(FULL, my_g, j)) group_p2 += w2;
+            }
+        }
         float s = in_p ? my_w2 : 0.f;
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
@@ -99,27 +123,51 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
     if (lane == 0) {
         out_len[row] = kept;
         // the rounding of the fp32 norm arithmetic is covered by the relative and absolute slack
-        const float xp = norm_p2 > 0.f ? sqrtf(norm_p2) * (1.f + 1e-5f) + 1e-6f : 0.f;
+        const float xp = norm_up(norm_p2);
         const float thr = threshold - margin - margin_per_feature * (float)kept;
         out_thr[row] = thr > 0.f ? thr : 0.f;
         out_xp[row] = xp;
     }
+    if (out_xg && lane < HEAVY_GROUPS) out_xg[row * HEAVY_GROUPS + lane] = __float2half_ru(norm_up(group_p2));
 }
 
 // norm of every row restricted to the heavy features (hrank >= 0), rounded up; one warp per row
 __global__ void heavy_norms_kernel(int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ indptr,
                                    const int32_t *__restrict__ idx, const float *__restrict__ val,
-                                   const int8_t *__restrict__ hrank, float *__restrict__ out) {
+                                   const int8_t *__restrict__ hrank, float *__restrict__ out,
+                                   __half *__restrict__ out_g) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
+    const int lane = lane_id();
     const int64_t row = row_begin + r;
     const int64_t p1 = indptr[row + 1];
     float s = 0.f;
-    for (int64_t p = indptr[row] + lane_id(); p < p1; p += 32)
-        if (hrank[idx[p]] >= 0) s = fmaf(val[p], val[p], s);
+    float group2 = 0.f;        // lanes 0..7: squared norm over the heavy features of group `lane`
+    for (int64_t base = indptr[row]; base < p1; base += 32) {
+        const int64_t p = base + lane;
+        int h = -1;
+        float w2 = 0.f;
+        if (p < p1) {
+            h = hrank[idx[p]];
+            if (h >= 0) {
+                w2 = val[p] * val[p];
+                s = fmaf(val[p], val[p], s);
+            }
+        }
+        if (out_g) {
+            unsigned hm = __ballot_sync(FULL, h >= 0);
+            while (hm) {
+                const int j = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const float o2 = __shfl_sync(FULL, w2, j);
+                if (lane == (__shfl_sync(FULL, h, j) >> 3)) group2 += o2;
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (lane_id() == 0) out[r] = s > 0.f ? sqrtf(s) * (1.f + 1e-5f) + 1e-6f : 0.f;
+    if (lane == 0) out[r] = norm_up(s);
+    if (out_g && lane < HEAVY_GROUPS) out_g[r * HEAVY_GROUPS + lane] = __float2half_ru(norm_up(group2));
 }
 
 // bound[t] = largest heavy norm among the right rows at positions [t*W, (t+1)*W) of the processing order
@@ -165,26 +213,28 @@ int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr, con
                   const float *val32, const int32_t *df_right, const int8_t *prunable, float right_norm,
                   float budget, float threshold, float margin, float margin_per_feature, int32_t *out_indices,
                   float *out_val32, int32_t *out_len, float *out_threshold, float *out_pruned_norm,
-                  void *stream_) {
+                  void *out_group_norms, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t n = row_end - row_begin;
     if (n <= 0) return SG_OK;
     if (!(budget >= 0.f) || !(right_norm >= 0.f)) return fail(SG_ERR_INVALID, "budget and right_norm must be >= 0");
+    if (out_group_norms && !prunable) return fail(SG_ERR_INVALID, "group norms need the heavy-feature ranks");
     prune_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, val32, df_right,
                                                               prunable, right_norm, budget, threshold, margin,
                                                               margin_per_feature, out_indices, out_val32, out_len,
-                                                              out_threshold, out_pruned_norm);
+                                                              out_threshold, out_pruned_norm,
+                                                              (__half *)out_group_norms);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }
 
 int sg_heavy_norms(int64_t row_begin, int64_t row_end, const int64_t *indptr, const int32_t *indices,
-                   const float *val32, const int8_t *hrank, float *out_norm, void *stream_) {
+                   const float *val32, const int8_t *hrank, float *out_norm, void *out_group_norms, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t n = row_end - row_begin;
     if (n <= 0) return SG_OK;
     heavy_norms_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(row_begin, n, indptr, indices, val32, hrank,
-                                                               out_norm);
+                                                               out_norm, (__half *)out_group_norms);
     SG_LAUNCH_CHECK();
     return SG_OK;
 }

@@ -18,7 +18,7 @@ print("n=%d nnz=%d V=%d" % (n, A.nnz, A.shape[1]), flush=True)
 res = {}
 for kernel in (["tiles", "row"] if which == "both" else [which]):
     for rep in range(reps):
-        A._order = None; A._postings2 = {}; A._tiles = None; A._df = None
+        A._order = None; A._postings2 = {}; A._tiles = None
         st = {"time_kernels": True}
         torch.cuda.synchronize(); t = time.time()
         got = D.cossim_topn(A, A, 20, 0.8, stats=st, kernel=kernel)
@@ -26,7 +26,7 @@ for kernel in (["tiles", "row"] if which == "both" else [which]):
         kms = sum(a.elapsed_time(b) for a, b in st["candidate_events"])
         print("%s rep %d: cossim_topn %.1f ms, candidates launch(es) %.2f ms, cand=%d above=%d nnz=%d pairs=%s postings=%s stage=%s prune=%s select=%s" % (
             kernel, rep, tk * 1e3, kms, st["n_candidates"], st["n_above_threshold"], got.nnz, st.get("pairs_walked"),
-            st.get("postings_walked"), st.get("stage_bytes"), st.get("prune"), st.get("select")), flush=True)
+            st.get("postings_walked"), st.get("stage_bytes"), st.get("prune"), st.get("select")), "refined=%s" % st.get("n_refined"), flush=True)
         print("   phases ms:", {k: round(v, 2) for k, v in D.phases_ms(st).items()}, flush=True)
     res[kernel] = got.host_triples()
 if len(res) == 2:

@@ -264,3 +264,62 @@ def test_nearest_master_matches_host_rule():
     want[c[order][first]] = r[order][first]
     assert np.array_equal(got, want)
     assert np.all(got[-100:] == -1)
+
+
+@pytest.mark.parametrize("thr,two", [(0.8, False), (0.6, False), (0.7, True)])
+def test_grouped_bound_refinement_changes_nothing_but_the_work(monkeypatch, thr, two):
+    """sg_rescore_refined drops candidates whose partial score plus the grouped Cauchy-Schwarz bound of the pruned part
+    cannot reach the row's threshold: same triples as the plain re-score of every candidate, fewer rows read."""
+    from string_grouper_b200 import _device as D
+    names = make_names(30000, seed=21)
+    master, dupes = (names[:20000], names[20000:]) if two else (names, None)
+    out = {}
+    for on in (False, True):
+        monkeypatch.setattr(D, "REFINE", on)
+        st = {}
+        _, _, ref, got = _run(master, dupes, 20, thr, stats=st, kernel="row")
+        out[on] = (got.host_triples(), st)
+    (a, st_off), (b, st_on) = out[False], out[True]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert "n_refined" not in st_off and st_on["n_candidates"] == st_off["n_candidates"]
+    assert st_on["n_above_threshold"] == st_off["n_above_threshold"] <= st_on["n_refined"] < 0.7 * st_on["n_candidates"]
+    cut = row_cutoffs(ref.indptr, ref.data, 20, len(master))
+    compare_triples(csr_triples(ref), b, len(master) if dupes is None else len(dupes), thr, cutoff_row=cut,
+                    label="refined")
+
+
+def test_group_norms_bound_the_heavy_part():
+    """fp16 group norms of sg_heavy_norms / sg_prune_rows: never below the fp64 norm of the group, within 0.2 % of it;
+    pruned features are heavy features and the groups partition them (8 ranks each)."""
+    from string_grouper_b200 import _device as D
+    P = _oracle()
+    names = make_names(6000, seed=3)
+    m, _, _ = P.tf_idf_matrices(names, None, dtype=np.float64)
+    A = D.DeviceCSR.from_scipy(m)
+    hrank, perm, rank = D.right_order(A)
+    hr = hrank.cpu().numpy().astype(np.int64)
+    yg = A._heavy_groups.float().cpu().numpy().reshape(-1, 8)
+    yh = A._heavy_norm.cpu().numpy()
+    csr = m.tocsr()
+    sq = csr.multiply(csr).tocsr()
+    for g in range(8):
+        cols = np.flatnonzero((hr >= 0) & (hr // 8 == g))
+        true = np.sqrt(np.asarray(sq[:, cols].sum(axis=1)).ravel())
+        assert np.all(yg[:, g] >= true) and np.all(yg[:, g] <= true * 1.002 + 2e-6), g
+    assert np.all(np.sqrt((yg.astype(np.float64) ** 2).sum(1)) >= yh * (1 - 1e-4))
+    p_idx, p_val, p_len, p_thr, p_xp, p_xg = D.prune_left(A, A, hrank, 0, A.shape[0], 0.8, D.CAND_MARGIN,
+                                                        D.U16_MARGIN_PER_FEATURE, 0.9)
+    xg = p_xg.float().cpu().numpy().reshape(-1, 8).astype(np.float64)
+    xp = p_xp.cpu().numpy()
+    kept_len = p_len.cpu().numpy()
+    kept_idx = p_idx.cpu().numpy()
+    indptr = m.indptr
+    assert (xp > 0).sum() > 1000
+    for r in np.flatnonzero(xp > 0)[:500]:
+        kept = set(kept_idx[indptr[r]:indptr[r] + kept_len[r]].tolist())
+        pruned = [(f, v) for f, v in zip(m.indices[indptr[r]:indptr[r + 1]], m.data[indptr[r]:indptr[r + 1]])
+                  if f not in kept]
+        assert pruned and all(hr[f] >= 0 for f, _ in pruned)
+        for g in range(8):
+            true = np.sqrt(sum(v * v for f, v in pruned if hr[f] // 8 == g))
+            assert true <= xg[r, g] <= true * 1.002 + 2e-6, (r, g)

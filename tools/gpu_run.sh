@@ -1,5 +1,6 @@
-python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; echo "rcsmoke=$?"; tail -1 gpurun_out/r2_final_smoke.log
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2_tests_final2.log 2>&1; echo "rctests=$?"
-tail -4 gpurun_out/r2_tests_final2.log
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_1gpu_final.json 2> gpurun_out/r2_bench_1gpu_final.err; echo "rcbench=$?"
-tail -c 300 gpurun_out/r2_bench_1gpu_final.err
+timeout 1200 python -m pytest tests/test_gpu_cossim.py tests/test_gpu_golden_synthetic.py tests/test_gpu_compat.py -q -m gpu -x > gpurun_out/r2o_tests.log 2>&1; echo "rctests=$?"; tail -15 gpurun_out/r2o_tests.log
+for v in 1 0; do
+  echo "== refine=$v"
+  SG_B200_REFINE=$v timeout 600 python tests/gpu_k2_compare.py 663000 row 3 2>&1 | grep -E "phases|rep 2"
+  SG_B200_REFINE=$v timeout 600 python tests/gpu_k2_compare.py 100000 row 3 2>&1 | grep -E "phases|rep 2" | tail -2
+done
