@@ -403,7 +403,8 @@ def main():
                 "filter_block_maxima_bytes": 2 * Tp * nnz_a_local,     # fp16 block maximum per (kept feature, tile) (L2)
                 "left_rows_bytes": 12 * nnz_a_local * max(1, (T + int(st.get("tiles_per_group") or T) - 1)
                                                           // int(st.get("tiles_per_group") or T)),
-                "candidate_bytes": 8 * int(st["n_candidates"])}
+                # row, column and (when the grouped bound re-tests them, `n_refined`) the partial score
+                "candidate_bytes": (12 if st.get("n_refined") is not None else 8) * int(st["n_candidates"])}
         streamed["total"] = int(sum(streamed.values()))
         streamed["pairs_walked"], streamed["postings_walked"] = pairs_w, post_w
         streamed["note"] = ("pairs / postings counted by sg::tile_candidates_kernel on the same input; upper bounds where "
@@ -435,7 +436,7 @@ def main():
                                 "gain_vs_streamed": (alg_bytes / bytes_real) if bytes_real else None},
                 "limiter": pipe,
                 "tile": {k: st.get(k) for k in ("kernel", "tile_w", "warps", "n_tiles", "stage_bytes", "n_candidates",
-                                                "n_above_threshold", "prune", "acc")}}
+                                                "n_refined", "n_above_threshold", "prune", "acc")}}
 
     if rank != 0:
         if world > 1:

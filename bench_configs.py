@@ -147,6 +147,7 @@ def main():
             "select": stats.get("select"),
             "accumulator": stats.get("acc"), "tile_w": stats.get("tile_w"), "warps": stats.get("warps"),
             "n_candidates_rank0": stats.get("n_candidates"),
+            "n_refined_rank0": stats.get("n_refined"),
             "n_above_threshold_rank0": stats.get("n_above_threshold")}), flush=True)
     if world > 1:
         dist.destroy_process_group()

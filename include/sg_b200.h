@@ -190,13 +190,14 @@ int sg_prune_rows(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[d
                   float budget, float threshold, float margin, float margin_per_feature,
                   int32_t *out_indices /*[dev]*/, float *out_val32 /*[dev]*/, int32_t *out_len /*[dev] per row id*/,
                   float *out_threshold /*[dev] per row id*/, float *out_pruned_norm /*[dev] per row id*/,
-                  void *out_group_norms /*[dev] fp16[8] per row id (16-byte aligned) or NULL: |x_P| per group of 8
-                                          heavy ranks, rounded up; needs `prunable` = sg_heavy_features ranks*/,
+                  void *out_group_norms /*[dev] fp16[16] per row id (32-byte aligned) or NULL: |x_P| per group of
+                                          heavy ranks (csrc/sg_prune.cu: ranks 0..13 alone, 14..38, 39..63), rounded
+                                          up; needs `prunable` = sg_heavy_features ranks*/,
                   void *stream);
 int sg_heavy_norms(int64_t row_begin, int64_t row_end, const int64_t *indptr /*[dev]*/,
                    const int32_t *indices /*[dev]*/, const float *val32 /*[dev]*/, const int8_t *hrank /*[dev]*/,
                    float *out_norm /*[dev] row_end-row_begin*/,
-                   void *out_group_norms /*[dev] fp16[8] per row of the range or NULL: |y_H| per group, rounded up*/,
+                   void *out_group_norms /*[dev] fp16[16] per row of the range or NULL: |y_H| per group, rounded up*/,
                    void *stream);
 int sg_tile_bounds(int64_t n_right, const int32_t *perm /*[dev] position -> row, or NULL*/,
                    const float *row_norm /*[dev] per row*/, int tile_w, float *bound /*[dev] n_tiles*/, void *stream);
@@ -315,8 +316,8 @@ int sg_rescore(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
  * were scored.  keep_count / keep_row / keep_col are required. */
 int sg_rescore_refined(int64_t n_cand, const int32_t *cand_row, const int32_t *cand_col,
                        const float *cand_partial /*[dev] n_cand*/,
-                       const void *left_group_norms /*[dev] fp16[8] per left row id*/,
-                       const void *right_group_norms /*[dev] fp16[8] per right row id*/,
+                       const void *left_group_norms /*[dev] fp16[16] per left row id*/,
+                       const void *right_group_norms /*[dev] fp16[16] per right row id*/,
                        const float *row_threshold /*[dev] per left row id*/,
                        const int64_t *a_indptr, const int32_t *a_indices, const void *a_val,
                        const int64_t *b_indptr, const int32_t *b_indices, const void *b_val, int dtype,

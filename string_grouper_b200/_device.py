@@ -144,7 +144,7 @@ class DeviceCSR:
         self.global_rows = None
         self._df = None             # document frequency of every feature (sg_feature_df)
         self._heavy_norm = None     # per-row norm over the heavy features (sg_heavy_norms)
-        self._heavy_groups = None   # the same per group of 8 heavy ranks, fp16 (sg_rescore_refined)
+        self._heavy_groups = None   # the same per group of heavy ranks, fp16[16] (sg_rescore_refined)
         self.nonneg = True          # no negative stored value (K1 output; checked for uploaded matrices)
 
     @property
@@ -234,13 +234,13 @@ def heavy_features(B):
 
 def heavy_norms(M, hrank, row_begin=0, row_end=None, groups=False):
     """fp32 norm of rows [row_begin,row_end) of M over the heavy features, rounded up (sg_heavy_norms); with
-    `groups` also the fp16 norms per group of 8 heavy ranks (8 per row): (norm, group_norms)."""
+    `groups` also the fp16 norms per group of heavy ranks (16 per row, csrc/sg_prune.cu): (norm, group_norms)."""
     t = require_cuda()
     L = _lib.load()
     row_end = M.shape[0] if row_end is None else row_end
     n = max(row_end - row_begin, 0)
     out = _empty(n, t.float32, M.device)
-    grp = _empty(8 * n, t.float16, M.device) if groups else None
+    grp = _empty(16 * n, t.float16, M.device) if groups else None
     _lib.check(L.sg_heavy_norms(row_begin, row_end, _ptr(M.d_indptr), _ptr(M.d_indices), _ptr(M.d_val32),
                                 _ptr(hrank), _ptr(out), _ptr(grp), _stream()))
     LAUNCH_COUNTS["prune"] += 1
@@ -443,7 +443,7 @@ def prune_left(A, B, hrank, row_begin, row_end, threshold, margin, margin_per_fe
     p_len = _empty(A.shape[0], t.int32, A.device)
     p_thr = _empty(A.shape[0], t.float32, A.device)
     p_xp = _empty(A.shape[0], t.float32, A.device)
-    p_xg = _empty(8 * A.shape[0], t.float16, A.device)      # |x_P| per group of 8 heavy ranks
+    p_xg = _empty(16 * A.shape[0], t.float16, A.device)     # |x_P| per group of heavy ranks
     budget = max(float(frac) * (float(threshold) - margin), 0.0)
     # the kernel works on left weights as stored and right rows of norm <= B.norm_bound
     _lib.check(L.sg_prune_rows(row_begin, row_end, _ptr(A.d_indptr), _ptr(A.d_indices), _ptr(A.d_val32), _ptr(df),

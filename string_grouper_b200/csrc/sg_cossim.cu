@@ -541,21 +541,25 @@ __global__ void __launch_bounds__(256, 8) rescore_kernel(int64_t n, const int32_
 }
 
 // sg_rescore_refined: a CTA takes REFINE_CHUNK consecutive candidates.  Pass 1 re-tests each with the grouped bound
-// (one 16-byte load of the column's group norms, the row's are shared by neighbours) and compacts the survivors'
+// (one 32-byte sector of the column's group norms, the row's are shared by neighbours) and compacts the survivors'
 // positions into shared memory; pass 2 scores the survivors with full warps, exactly as rescore_kernel does.
 constexpr int REFINE_CHUNK = 2048;
 
-__device__ __forceinline__ float group_dot(const uint4 &x, const uint4 &y) {
+__device__ __forceinline__ float group_dot8(const uint4 &x, const uint4 &y, float d) {
     const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
     const __half2 *yh = reinterpret_cast<const __half2 *>(&y);
-    float d = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float2 a = __half22float2(xh[k]), b = __half22float2(yh[k]);
         d = fmaf(a.x, b.x, d);          // products of two fp16 values are exact in fp32
         d = fmaf(a.y, b.y, d);
     }
-    return d * (1.f + 1e-5f) + 1e-6f;   // the eight fp32 additions, rounded up
+    return d;
+}
+// sum over the 16 groups of |x_P,g| |y_H,g| (fp16[16] per row, csrc/sg_prune.cu), the fp32 additions rounded up
+__device__ __forceinline__ float group_dot(const uint4 *__restrict__ x, const uint4 *__restrict__ y) {
+    const float d = group_dot8(x[1], __ldg(y + 1), group_dot8(x[0], __ldg(y), 0.f));
+    return d * (1.f + 1e-5f) + 1e-6f;
 }
 
 template <typename T, int VEC>
@@ -580,7 +584,7 @@ rescore_refined_kernel(int64_t n, const int32_t *__restrict__ cr, const int32_t 
         bool pass = false;
         if (i < n) {
             const int32_t r = cr[i], c = cc[i];
-            pass = partial[i] + group_dot(xg[r], __ldg(yg + c)) > thr_row[r];
+            pass = partial[i] + group_dot(xg + 2 * (int64_t)r, yg + 2 * (int64_t)c) > thr_row[r];
         }
         const unsigned m = __ballot_sync(FULL, pass);
         if (m) {
@@ -939,8 +943,8 @@ int sg_rescore_refined(int64_t n_cand, const int32_t *cand_row, const int32_t *c
     if (!keep_count || !keep_row || !keep_col) return fail(SG_ERR_INVALID, "keep_count, keep_row and keep_col are required");
     if (!cand_partial || !left_group_norms || !right_group_norms || !row_threshold)
         return fail(SG_ERR_INVALID, "partial scores, group norms and row thresholds are required");
-    if (((uintptr_t)left_group_norms | (uintptr_t)right_group_norms) & 15)
-        return fail(SG_ERR_INVALID, "group norms must be 16-byte aligned");
+    if (((uintptr_t)left_group_norms | (uintptr_t)right_group_norms) & 31)
+        return fail(SG_ERR_INVALID, "group norms must be 32-byte aligned");
     const unsigned grid = (unsigned)((n_cand + REFINE_CHUNK - 1) / REFINE_CHUNK);
     const bool vec = ((uintptr_t)b_indices & 15) == 0;
 #define SG_RESCORE(T, VEC)                                                                                         \

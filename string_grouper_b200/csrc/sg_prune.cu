@@ -18,18 +18,22 @@
 // largest |y_H| inside a column tile (sg_tile_bounds) is close to that of each of its columns and the
 // candidate threshold of (row i, tile t) becomes  threshold - |x_P(i)| * bound(t).
 //
-// Tighter again, per candidate: H is split into SG_HEAVY_GROUPS groups by rank (8 ranks each).  With x_P,g / y_H,g the
-// parts of x_P / y_H in group g,  x_P . y = sum_g x_P,g . y_H,g <= sum_g |x_P,g| |y_H,g|.  sg_prune_rows and
-// sg_heavy_norms store the group norms (fp16, rounded up, 16 bytes per row); sg_rescore_refined re-tests every
-// candidate (row i, column j) with  partial score > threshold(i) - sum_g |x_P,g(i)| |y_H,g(j)|  before it reads the
-// right row: on the 663k benchmark 9 of 10 false candidates of the tile-wide bound go (profiles/r2_notes.md).
+// Tighter again, per candidate: H is split into 16 groups by rank — the 14 most frequent features one group each
+// (what gets pruned is almost always among them, and for a group of one the bound is the product itself), ranks
+// 14..38 and 39..63 one group each.  With x_P,g / y_H,g the parts of x_P / y_H in group g,
+// x_P . y = sum_g x_P,g . y_H,g <= sum_g |x_P,g| |y_H,g|.  sg_prune_rows and sg_heavy_norms store the group norms
+// (fp16, rounded up, 32 bytes = one sector per row); sg_rescore_refined re-tests every candidate (row i, column j)
+// with  partial score > threshold(i) - sum_g |x_P,g(i)| |y_H,g(j)|  before it reads the right row.  Candidates per
+// left row on the 663k benchmark (sample): tile-wide bound 501, 8 groups of 8 ranks 85, this grouping 45, pairs
+// above the threshold 42 (profiles/r2_notes.md).
 #include <cuda_fp16.h>
 
 #include "sg_common.cuh"
 
 namespace sg {
 
-constexpr int HEAVY_GROUPS = 8;        // 64 heavy ranks / 8
+constexpr int HEAVY_GROUPS = 16;
+__device__ __forceinline__ int heavy_group(int rank) { return rank < 14 ? rank : (rank < 39 ? 14 : 15); }
 
 // fp32 norm from a sum of squares, rounded up: relative and absolute slack cover the fp32 arithmetic
 __device__ __forceinline__ float norm_up(float s2) { return s2 > 0.f ? sqrtf(s2) * (1.f + 1e-5f) + 1e-6f : 0.f; }
@@ -62,7 +66,7 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
     const float lim2 = lim * lim;
     int kept = 0;
     float norm_p2 = 0.f;
-    float group_p2 = 0.f;      // lanes 0..7: squared norm of the pruned features of group `lane`
+    float group_p2 = 0.f;      // lanes 0..15: squared norm of the pruned features of group `lane`
     for (int base = 0; base < nf; base += 32) {
         const int k = base + lane;
         float my_key = -1.f, my_w2 = 0.f, my_v = 0.f;
@@ -106,7 +110,7 @@ __global__ void prune_rows_kernel(int64_t row_begin, int64_t n_rows, const int64
         }
         kept += __popc(km);
         if (out_xg) {          // pruned features are few: one at a time, the lane of its group adds it
-            const int my_g = in_p ? (int)prunable[my_f] >> 3 : 0;
+            const int my_g = in_p ? heavy_group((int)prunable[my_f]) : 0;
             unsigned pm = __ballot_sync(FULL, in_p);
             while (pm) {
                 const int j = __ffs(pm) - 1;
@@ -142,7 +146,7 @@ __global__ void heavy_norms_kernel(int64_t row_begin, int64_t n_rows, const int6
     const int64_t row = row_begin + r;
     const int64_t p1 = indptr[row + 1];
     float s = 0.f;
-    float group2 = 0.f;        // lanes 0..7: squared norm over the heavy features of group `lane`
+    float group2 = 0.f;        // lanes 0..15: squared norm over the heavy features of group `lane`
     for (int64_t base = indptr[row]; base < p1; base += 32) {
         const int64_t p = base + lane;
         int h = -1;
@@ -160,7 +164,7 @@ __global__ void heavy_norms_kernel(int64_t row_begin, int64_t n_rows, const int6
                 const int j = __ffs(hm) - 1;
                 hm &= hm - 1;
                 const float o2 = __shfl_sync(FULL, w2, j);
-                if (lane == (__shfl_sync(FULL, h, j) >> 3)) group2 += o2;
+                if (lane == heavy_group(__shfl_sync(FULL, h, j))) group2 += o2;
             }
         }
     }

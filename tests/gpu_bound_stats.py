@@ -37,9 +37,16 @@ def group_norms(gid_of_rank, G):
     Gm[torch.arange(V, device=dev)[heavy], g[heavy]] = 1.0
     return Y.view(n, G).sqrt() * (1 + 1e-6), Gm
 
-schemes = {"1 group": (lambda r: r * 0, 1), "4 by rank range": (lambda r: r // 16, 4), "4 interleaved": (lambda r: r % 4, 4),
-           "8 by rank range": (lambda r: r // 8, 8), "8 interleaved": (lambda r: r % 8, 8),
-           "16 interleaved": (lambda r: r % 16, 16), "64 (exact support)": (lambda r: r, 64)}
+def singles(k, rest):          # ranks 0..k-1 alone, the others in `rest` equal ranges
+    width = -(-(64 - k) // rest)
+    return lambda r: torch.where(r < k, r, k + (r - k) // width)
+
+schemes = {"8 by rank range": (lambda r: r // 8, 8), "16 by rank range": (lambda r: r // 4, 16),
+           "8 = 6 singles + 2": (singles(6, 2), 8), "8 = 7 singles + 1": (singles(7, 1), 8),
+           "8 = 4 singles + 4": (singles(4, 4), 8),
+           "16 = 12 singles + 4": (singles(12, 4), 16), "16 = 14 singles + 2": (singles(14, 2), 16),
+           "16 = 8 singles + 8": (singles(8, 8), 16), "32 = 24 singles + 8": (singles(24, 8), 32),
+           "64 (exact support)": (lambda r: r, 64)}
 norms = {k: group_norms(f, G) for k, (f, G) in schemes.items()}
 R = 256
 tot = {}

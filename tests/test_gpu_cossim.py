@@ -290,7 +290,7 @@ def test_grouped_bound_refinement_changes_nothing_but_the_work(monkeypatch, thr,
 
 def test_group_norms_bound_the_heavy_part():
     """fp16 group norms of sg_heavy_norms / sg_prune_rows: never below the fp64 norm of the group, within 0.2 % of it;
-    pruned features are heavy features and the groups partition them (8 ranks each)."""
+    pruned features are heavy features and the 16 groups partition them (ranks 0..13 alone, 14..38, 39..63)."""
     from string_grouper_b200 import _device as D
     P = _oracle()
     names = make_names(6000, seed=3)
@@ -298,18 +298,19 @@ def test_group_norms_bound_the_heavy_part():
     A = D.DeviceCSR.from_scipy(m)
     hrank, perm, rank = D.right_order(A)
     hr = hrank.cpu().numpy().astype(np.int64)
-    yg = A._heavy_groups.float().cpu().numpy().reshape(-1, 8)
+    grp = np.where(hr < 14, hr, np.where(hr < 39, 14, 15))
+    yg = A._heavy_groups.float().cpu().numpy().reshape(-1, 16)
     yh = A._heavy_norm.cpu().numpy()
     csr = m.tocsr()
     sq = csr.multiply(csr).tocsr()
-    for g in range(8):
-        cols = np.flatnonzero((hr >= 0) & (hr // 8 == g))
+    for g in range(16):
+        cols = np.flatnonzero((hr >= 0) & (grp == g))
         true = np.sqrt(np.asarray(sq[:, cols].sum(axis=1)).ravel())
         assert np.all(yg[:, g] >= true) and np.all(yg[:, g] <= true * 1.002 + 2e-6), g
     assert np.all(np.sqrt((yg.astype(np.float64) ** 2).sum(1)) >= yh * (1 - 1e-4))
     p_idx, p_val, p_len, p_thr, p_xp, p_xg = D.prune_left(A, A, hrank, 0, A.shape[0], 0.8, D.CAND_MARGIN,
                                                         D.U16_MARGIN_PER_FEATURE, 0.9)
-    xg = p_xg.float().cpu().numpy().reshape(-1, 8).astype(np.float64)
+    xg = p_xg.float().cpu().numpy().reshape(-1, 16).astype(np.float64)
     xp = p_xp.cpu().numpy()
     kept_len = p_len.cpu().numpy()
     kept_idx = p_idx.cpu().numpy()
@@ -320,6 +321,6 @@ def test_group_norms_bound_the_heavy_part():
         pruned = [(f, v) for f, v in zip(m.indices[indptr[r]:indptr[r + 1]], m.data[indptr[r]:indptr[r + 1]])
                   if f not in kept]
         assert pruned and all(hr[f] >= 0 for f, _ in pruned)
-        for g in range(8):
-            true = np.sqrt(sum(v * v for f, v in pruned if hr[f] // 8 == g))
+        for g in range(16):
+            true = np.sqrt(sum(v * v for f, v in pruned if grp[f] == g))
             assert true <= xg[r, g] <= true * 1.002 + 2e-6, (r, g)
