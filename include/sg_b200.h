@@ -141,11 +141,11 @@ int64_t sg_num_tiles(int64_t n_right, int tile_w);
 int64_t sg_num_tiles_padded(int64_t n_right, int tile_w);
 
 /*
- * Right matrix -> tile-major, column-sorted postings (the transpose that sp_matmul_topn performs on
+ * Right matrix -> tile-major postings (the transpose that sp_matmul_topn performs on
  * `Bi.T`, sg.py:727/:738, done once and laid out for the kernel).  The right rows are taken in the
  * order `rank` (position of every row in heavy-feature signature order, sg_row_order; NULL = input
  * order): column tile t holds positions [t*tile_w, (t+1)*tile_w); bucket (f, t) = the docs of feature f
- * inside tile t, sorted by position, at bucket_ptr[f*T + t] (feature-major, T = sg_num_tiles); a posting is 4 bytes:
+ * inside tile t (in no particular order), at bucket_ptr[f*T + t] (feature-major, T = sg_num_tiles); a posting is 4 bytes:
  * position - t*tile_w in the low 16 bits, the weight rounded to fp16 in the high 16 bits (candidate
  * scores only need to be within the caller's margin; every candidate is re-scored exactly).  `bucket_dir` (optional) receives the same directory as aligned
  * 8-byte entries {int32 start, u16 length, fp16 largest |weight| of the bucket}, T*(n_cols+1) of them, the form

@@ -327,7 +327,7 @@ def right_side(B, tile_w):
                                        _ptr(rank), tile_w, B.base, 1.0 / max(B.norm_bound, 1.0), _ptr(bucket_ptr),
                                        _ptr(bucket_dir), _ptr(bucket_maxw), _ptr(post),
                                        _ptr(ws), ws_bytes, _stream()))
-        LAUNCH_COUNTS["postings"] += 3
+        LAUNCH_COUNTS["postings"] += 4
         bound = t.zeros(Tp, dtype=t.float32, device=B.device)
         _lib.check(L.sg_tile_bounds(n_rows, _ptr(perm), _ptr(B._heavy_norm), tile_w, _ptr(bound), _stream()))
         LAUNCH_COUNTS["prune"] += 1
