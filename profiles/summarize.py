@@ -43,7 +43,7 @@ def rep(path):
         for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:14]:
             print("    %6.2f%% samples  %6.2f%% inst  wavefronts=%-12s %s" % (
                 100.0 * int(r[ix["# Samples"]]) / max(tot_s, 1), 100.0 * int(r[ix["Instructions Executed"]]) / max(tot_i, 1),
-                r[ix["L1 Wavefronts Shared"]], r[ix["Source"]].strip()[:70]))
+                r[ix["L1 Wavefronts Shared"]] if "L1 Wavefronts Shared" in ix else "-", r[ix["Source"]].strip()[:70]))
 
 
 def launch_list(path):
