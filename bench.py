@@ -41,15 +41,26 @@ TOP_N, MIN_SIM = 20, 0.8
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe).
+
+    start() launches the process early (its NVML initialisation enumerates every GPU of the box and was seen to
+    stall rank 0 for 10-15 ms when it fell into a timed step of an 8-GPU run); arm() marks the beginning of the timed
+    region: only samples from then on (and the one just before) are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.t_arm = gpu_index, [], None, None
+
+    def arm(self):
+        if self.proc is None:
+            self.start()
+        self.t_arm = time.time()
 
     def start(self):
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -60,14 +71,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, power, reasons = [], [], [], set()
-        for r in self.rows:
+        rows = list(self.rows)
+        if self.t_arm is not None:
+            before = [r for t, r in rows if t < self.t_arm][-1:]
+            rows = before + [r for t, r in rows if t >= self.t_arm]
+        else:
+            rows = [r for _, r in rows]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
             except Exception:
@@ -189,6 +206,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # long before the timed region, see ClockSampler
     if world > 1:
         os.environ.setdefault("SG_B200_DISTRIBUTED", "1")     # the library shards only when told to
         dist.init_process_group("nccl", device_id=dev)
@@ -231,7 +251,6 @@ def main():
     # ---- device-resident throughput ("value") ----
     step_ms, cand_ms, pairs = [], [], 0
     launches0 = None
-    sampler = ClockSampler(local_rank)
     S = None
     for step in range(args.warmup + args.steps):
         flush.zero_()
@@ -240,7 +259,7 @@ def main():
         if timed and launches0 is None:
             launches0 = dict(D.LAUNCH_COUNTS)
             if rank == 0:
-                sampler.start()
+                sampler.arm()
         stats = {"time_kernels": True}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
