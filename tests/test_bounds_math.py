@@ -5,6 +5,7 @@ fails on CPU already.
 
   (1) pruning:    x.y <= |x_P| * |y_H| + x_S.y         for P a subset of the heavy features H
   (2) block max:  x_S.y_j <= sum_f |x_f| * max_{j' in tile(j)} |y_j'f|
+  (3) grouped:    x_P.y <= sum_g |x_P,g| * |y_H,g|     over the 16 groups of heavy ranks (sg_rescore_refined)
 """
 import numpy as np
 import scipy.sparse as sp
