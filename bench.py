@@ -20,6 +20,7 @@ One step = one pass of the hot path: K1 vectorise -> K2 top-n cosine product -> 
   cpu_baseline the CPU port's measured whole job on this box's usable cores (N=1)
 """
 import argparse
+import atexit
 import hashlib
 import json
 import os
@@ -65,9 +66,17 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            atexit.register(self._kill)          # never leave the sampler behind, whatever ends the run
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _kill(self):
+        try:
+            if self.proc is not None and self.proc.poll() is None:
+                self.proc.terminate()
+        except Exception:
+            pass
 
     def _read(self):
         for line in self.proc.stdout:
