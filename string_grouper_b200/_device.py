@@ -305,7 +305,7 @@ def right_tiles(B):
 
 
 def right_side(B, tile_w):
-    """Row order (heavy norm, signature), feature-major column-sorted postings, bucket directory with block maxima and
+    """Row order (heavy norm, signature), feature-major bucketed postings, bucket directory with block maxima and
     per-tile pruning bounds of the right matrix, cached on B."""
     t = require_cuda()
     L = _lib.load()

@@ -9,7 +9,8 @@
 //   candidates       block-max test of 64 tiles at a time, then the Gustavson row-wise product of the pruned left
 //                    row over the surviving tiles into a shared-memory accumulator tile per warp (16-bit fixed
 //                    point or fp32); emits (row, col) with partial score > the (row, tile) candidate threshold
-//   rescore          exact sorted-merge dot product of every candidate pair
+//   rescore          exact sorted-merge dot product of every candidate pair; rescore_refined first drops the
+//                    candidates whose partial score + grouped bound of the pruned part cannot reach the threshold
 //   topn_select      strict threshold, top-n per row, value-descending
 #include <cub/cub.cuh>
 #include <cuda_fp16.h>
@@ -19,7 +20,7 @@
 namespace sg {
 
 // ---------------------------------------------------------------------------
-// postings build: feature-major buckets (feature, column tile), column-sorted, in the processing order of the right rows
+// postings build: feature-major buckets (feature, column tile) over the processing order of the right rows
 // ---------------------------------------------------------------------------
 // bucket = f * T + t (feature-major: the buckets a left row walks for one of its features over consecutive column
 // tiles are neighbours in the directory and in the posting array), t = rank[doc] / tile_w.
